@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the dense flow-field hot path on B200.
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8(d) cfg 2): backward warp of a 1080p batch of 64 by a
+'target'-referenced flow with validity tracking, forward + backward, fp32 --
+
+    out, valid = Flow(flow, 't', mask).apply(img, tmask, return_valid_area=True);  out.backward(g)
+
+Metric: Mpix/s, flow-field pixels N*H*W per step.  One "step" is that call sequence on one batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+
+* `value`   : inputs resident in HBM, CUDA-event timed, max over ranks.
+* `e2e`     : same call through the public API with HOST (pinned) buffers: every step copies flow, image, both masks
+              and the upstream gradient host->device and the warped image, validity mask and both gradients
+              device->host inside the timed region.
+* `roofline`: the dominant kernel's algorithmic bytes / its CUDA-event duration measured live in the timed region,
+              against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* `cpu_baseline`: the CPU oracle (a C/OpenMP port of the reference's CPU path, oracle/) on a bounded sample.
+* `--impl reference`: only the CPU arm, as its own JSON line.
+
+Multi-GPU: one process per GPU (torchrun), the batch dimension is sharded, every rank runs the same per-GPU
+workload on its own shard (weak scaling), no collective on the data path; the time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, W, C = 1080, 1920, 3
+BYTES_PER_PX = {  # algorithmic bytes per flow pixel, SURVEY.md section 8(d), C = 3, with both masks
+    'ofb_warp_t_fwd': 8 * C + 10 + 1,      # flow 8 + payload 4C + 2 masks -> out 4C + valid 1      = 35
+    'ofb_warp_t_bwd': 12 * C + 16,         # gout 4C + flow 8 + payload 4C -> gflow 8 + gpayload 4C = 52
+    'ofb_flow_stats': 8 + 1,               # flow 8 + mask 1
+}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def known_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(p) as fh:
+            return json.load(fh).get(name)
+    except Exception:
+        return None
+
+
+def smooth_flow(n, h, w, sigma, seed, device):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    lo = (torch.randn(n, 2, h // 64 + 2, w // 64 + 2, generator=g) * sigma).to(device)
+    return torch.nn.functional.interpolate(lo, size=(h, w), mode='bicubic', align_corners=True).contiguous()
+
+
+def make_inputs(n, device, seed0=2):
+    """SURVEY.md 8(d) cfg 2: smooth-random flow sigma = 8 px, uniform image, holed masks; synthetic."""
+    flow = smooth_flow(n, H, W, 8.0, seed0, device)
+    g = torch.Generator(device=device).manual_seed(seed0 + 1)
+    img = torch.rand(n, C, H, W, generator=g, device=device)
+    gout = torch.rand(n, C, H, W, generator=g, device=device)
+    mask = torch.ones(n, H, W, dtype=torch.bool, device=device)
+    mask[:, 300:500, 700:1100] = False
+    mask[:, :, ::97] = False
+    tmask = mask.roll(131, dims=2)
+    return flow, img, mask, tmask, gout
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(nme)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_arm(steps, warmup, sample_n):
+    """The reference's CPU path, as restated by the oracle (C + OpenMP over all host cores), on a bounded sample of
+    the same workload: batch `sample_n` instead of 64 (the metric is per pixel and flat in N)."""
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    flow, img, mask, tmask, gout = make_inputs(sample_n, 'cpu')
+    times = []
+    for it in range(warmup + steps):
+        f = flow.clone().requires_grad_()
+        i = img.clone().requires_grad_()
+        t0 = time.perf_counter()
+        out, valid = orc.OFlow(f, 't', mask).apply(i, tmask, return_valid_area=True)
+        out.backward(gout)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    px = sample_n * H * W
+    return {'value': px / (ms * 1e-3) / 1e6, 'ms_per_step': ms, 'cores': cores, 'sample_n': sample_n}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def gpu_step(of, flow, img, mask, tmask, gout):
+    f = flow.requires_grad_()
+    i = img.requires_grad_()
+    out, valid = of.Flow(f, 't', mask).apply(i, tmask, return_valid_area=True)
+    out.backward(gout)
+    gf, gi = f.grad, i.grad
+    f.grad = None
+    i.grad = None
+    return out, valid, gf, gi
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='per-GPU batch (the named config is 64)')
+    ap.add_argument('--cpu-sample', type=int, default=4, help='batch of the bounded CPU sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    workload = 'Flow.apply ref t + target mask + valid area, fwd+bwd (grads to flow and image), %dx%dx%dx%d fp32' % (
+        args.batch, C, H, W)
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        r = cpu_reference_arm(args.steps, args.warmup, args.cpu_sample)
+        line = {
+            'impl': 'reference', 'metric': 'Mpix/s apply_flow fwd+bwd', 'value': r['value'], 'unit': 'Mpix/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload, 'sample': 'batch %d of 64 per step, same H, W, C' % r['sample_n']},
+            'cpu_baseline': {'value': r['value'], 'unit': 'Mpix/s', 'cores': r['cores'], 'kind': 'port',
+                             'sample': 'oracle (C/OpenMP restatement of the reference CPU path), batch %d x 1080p, '
+                                       'fwd+bwd, mean of %d steps' % (r['sample_n'], args.steps)},
+            'e2e': {'value': r['value'], 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+        }
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    import oflibpytorch_b200 as of
+    from oflibpytorch_b200 import _native, _ops
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.batch
+    px = n * H * W
+    flow, img, mask, tmask, gout = make_inputs(n, dev, seed0=2 + 10 * rank)
+
+    # ---------------------------------------------------------------- device-resident timing
+    for _ in range(args.warmup):
+        gpu_step(of, flow, img, mask, tmask, gout)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _native.launch_count_reset()
+    _ops.PROFILE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        gpu_step(of, flow, img, mask, tmask, gout)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _native.launch_count()
+    prof, _ops.PROFILE = _ops.PROFILE, None
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    per_kernel = {}
+    for name, a, b in prof:
+        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
+    peak, peak_src = measured_peak()
+    kernels = {}
+    for name, ts in per_kernel.items():
+        avg = sum(ts) / len(ts)
+        byts = BYTES_PER_PX.get(name, 0) * px
+        kernels[name] = {'ms': avg, 'calls_per_step': len(ts) / args.steps, 'algorithmic_bytes': byts,
+                         'gbs': byts / (avg * 1e-3) / 1e9}
+    dominant = max(kernels, key=lambda k: kernels[k]['ms'] * kernels[k]['calls_per_step'])
+    dk = kernels[dominant]
+    roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': dk['gbs'], 'peak': peak, 'unit': 'GB/s',
+                'frac': dk['gbs'] / peak, 'traffic': known_traffic(dominant), 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': dk['algorithmic_bytes'], 'ms_per_launch': dk['ms'],
+                'share_of_step': dk['ms'] * dk['calls_per_step'] / ms,
+                'all_kernels': {k: {'ms': round(v['ms'], 4), 'gbs': round(v['gbs'], 1),
+                                    'frac': round(v['gbs'] / peak, 4)} for k, v in kernels.items()},
+                'step_frac': (sum(BYTES_PER_PX[k] for k in ('ofb_warp_t_fwd', 'ofb_warp_t_bwd')) * px /
+                              (ms * 1e-3) / 1e9) / peak}
+
+    # ---------------------------------------------------------------- end to end with host buffers
+    e2e = None
+    if not args.no_e2e:
+        host_in = [x.detach().cpu().pin_memory() for x in (flow, img, mask, tmask, gout)]
+        o, v, gf, gi = gpu_step(of, flow, img, mask, tmask, gout)
+        host_out = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (o, v, gf, gi)]
+        del o, v, gf, gi
+        h2d = sum(x.numel() * x.element_size() for x in host_in)
+        d2h = sum(x.numel() * x.element_size() for x in host_out)
+
+        def e2e_step():
+            d = [x.to(dev, non_blocking=True) for x in host_in]
+            outs = gpu_step(of, d[0], d[1], d[2], d[3], d[4])
+            for dst, src in zip(host_out, outs):
+                dst.copy_(src, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        k2 = max(3, min(args.steps, 5))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(k2):
+            e2e_step()
+        s1.record()
+        barrier()
+        t2 = torch.tensor([s0.elapsed_time(s1) / k2], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * px / (float(t2.item()) * 1e-3) / 1e6, 'unit': 'Mpix/s',
+               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': float(t2.item()),
+               'steps': k2}
+        del host_in, host_out
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_arm(3, 1, args.cpu_sample)
+        cpu = {'value': r['value'], 'unit': 'Mpix/s', 'cores': r['cores'], 'kind': 'port',
+               'sample': 'oracle (C/OpenMP restatement of the reference CPU path), batch %d x 1080p, fwd+bwd, '
+                         'mean of 3 steps' % r['sample_n']}
+
+    if rank == 0:
+        line = {
+            'metric': 'Mpix/s apply_flow fwd+bwd', 'value': world * px / (ms_max * 1e-3) / 1e6, 'unit': 'Mpix/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload, 'per_gpu_batch': n, 'global_batch': n * world,
+                       'parallelism': 'batch shards, one per GPU, no collective',
+                       'l2': 'inputs (%.1f GB per step) exceed the 126 MB L2; no flush needed' % (
+                           (BYTES_PER_PX['ofb_warp_t_fwd'] + BYTES_PER_PX['ofb_warp_t_bwd']) * px / 1e9)},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

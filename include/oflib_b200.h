@@ -1,0 +1,132 @@
+/*
+ * oflib_b200.h -- C ABI of the B200-native dense flow-field hot path.
+ *
+ * The reference (oflibpytorch 2.1.1) has no FFI layer: its hot path is Python that calls
+ * torch.nn.functional.grid_sample (utils.py:555) and Tensor.scatter_add_ (utils.py:1133,1139).
+ * Each entry point below replaces one of those call sites together with the elementwise glue
+ * around it; the reference-side binding (ctypes) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers on the current CUDA device; tensors are dense, row-major
+ *     "planar" NCHW / NHW as in the reference ((N,2,H,W) flows, (N,C,H,W) payloads, (N,H,W) masks);
+ *   - masks are 1 byte per pixel, 0 or 1 (torch.bool storage);
+ *   - a "*_bs" argument is the batch stride of that tensor in ELEMENTS; 0 broadcasts one item over
+ *     the batch (the reference's 1<->N batch broadcasting, utils.py:527-537);
+ *   - optional pointers may be NULL where the comment says so;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream;
+ *   - the return value is 0 on success, a positive cudaError_t, or a negative OFB_E* code;
+ *     ofb_error_string() renders either.  No call allocates, synchronises or throws.
+ *   - fp32 arithmetic, IEEE division, no fast-math; the operation order is that of oracle/oracle.c
+ *     (SURVEY.md Appendix A), which is what makes the boolean outputs bit-exact.
+ */
+#ifndef OFLIB_B200_H
+#define OFLIB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFB_ABI_VERSION 1
+
+#define OFB_EINVAL (-1)   /* bad argument (NULL where required, non-positive size, C too large) */
+#define OFB_ESHAPE (-2)   /* H < 2 or W < 2: the reference divides by (W-1), (H-1) (utils.py:463-464) */
+
+/* bits written by ofb_flow_stats, one int32 per batch item */
+#define OFB_STAT_NONFINITE   1   /* some component is NaN/Inf            (utils.py:98)            */
+#define OFB_STAT_NONZERO     2   /* some component != 0                  (utils.py:938, thresholded=False) */
+#define OFB_STAT_NONZERO_T   4   /* some |component| >= 1e-3             (utils.py:642,938)        */
+#define OFB_STAT_NONZERO_M   8   /* as NONZERO,   only where mask is set (flow_class.py:1243)      */
+#define OFB_STAT_NONZERO_TM 16   /* as NONZERO_T, only where mask is set                           */
+
+/* validity rules for ofb_splat_s_fwd */
+#define OFB_VALID_NONE 0
+#define OFB_VALID_GT   1   /* mask channel > 0.99999   (flow_class.py:922)        */
+#define OFB_VALID_EQ1  2   /* mask channel == 1        (flow_class.py:1117,1170)  */
+
+int ofb_abi_version(void);
+const char *ofb_error_string(int status);
+
+/* Number of kernels this library has launched since load / since the last reset (host counter,
+ * used by bench.py for its "gpu_launches" claim). */
+int64_t ofb_launch_count(void);
+void ofb_launch_count_reset(void);
+
+/* One pass over a flow field: replaces get_valid_vecs' isfinite().all() (utils.py:98), is_zero_flow
+ * (utils.py:919-938) and Flow.is_zero (flow_class.py:1226-1244).  flags[N] must be zero on entry and
+ * receives the OR of the OFB_STAT_* bits per batch item.  mask (N,H,W) may be NULL (then the *_M
+ * bits equal the unmasked ones). */
+int ofb_flow_stats(const float *flow, const uint8_t *mask, int32_t *flags,
+                   int N, int H, int W, void *stream);
+
+/* W -- backward warp of a payload by a target-referenced flow, with fused validity.
+ * Replaces apply_flow(ref='t') (utils.py:541-555: grid - flow, normalise_coords, grid_sample(bilinear,
+ * zeros, align_corners=True)) and, when `valid` is given, the mask tracking of Flow.apply
+ * (flow_class.py:896-898,922-934): the payload mask travels as a 0/1 channel through the same weights
+ * and  valid = (warped mask channel > valid_thresh) & flow_mask.
+ *   sample position   p - flow_sign * flow(p)            (flow_sign = -1 restates apply_flow(-vecs, ..))
+ *   out[c]            bilinear(src[c]) (+ add_flow * flow[c] when C == 2: combine mode 3,
+ *                                       flow_class.py:1804,1808)
+ *   src      (N|1, C, H, W)  may be NULL iff C == 0 (validity only: valid_target/valid_source 't')
+ *   src_mask (N|1, H, W)     NULL = all true           flow_mask (N|1, H, W)  NULL = all true
+ *   out      (N, C, H, W)    may be NULL iff C == 0    valid (N, H, W)        NULL = not wanted */
+int ofb_warp_t_fwd(const float *flow, int64_t flow_bs, float flow_sign,
+                   const float *src, int64_t src_bs,
+                   const uint8_t *src_mask, int64_t src_mask_bs,
+                   const uint8_t *flow_mask, int64_t flow_mask_bs,
+                   float add_flow, float valid_thresh,
+                   float *out, uint8_t *valid,
+                   int N, int C, int H, int W, void *stream);
+
+/* Adjoint of ofb_warp_t_fwd with respect to flow and src (replaces grid_sampler_2d_backward and the
+ * backward of normalise_coords).  gflow (N,2,H,W) and gsrc may each be NULL.  gsrc has batch stride
+ * gsrc_bs (0 accumulates a broadcast payload's gradient over the batch) and is zero-filled by the
+ * call before accumulation.  With add_flow != 0 (C == 2) gflow also receives add_flow * gout. */
+int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sign,
+                   const float *src, int64_t src_bs,
+                   const float *gout, float add_flow,
+                   float *gflow, float *gsrc, int64_t gsrc_bs,
+                   int N, int C, int H, int W, void *stream);
+
+/* S -- normalised bilinear forward splat.  Replaces get_flow_endpoints (utils.py:1045-1058),
+ * grid_from_unstructured_data (utils.py:1061-1154) and apply_s_flow (utils.py:1157-1205), and, with
+ * `data_mask`/`valid`, the mask tracking of Flow.apply for 's' flows (flow_class.py:880-898,922).
+ *   coordinates   relative != 0:  x = sign*cx + j, y = sign*cy + i  (cx, cy = the two planes of a flow)
+ *                 relative == 0:  x = cx, y = cy                     (grid_from_unstructured_data)
+ *   cx, cy    (N|1, H, W) planes, batch stride coord_bs
+ *   data      (N|1, C, H, W), C may be 0 (then data/out may be NULL)
+ *   data_mask (N|1, H, W) the 0/1 "mask channel" splatted along with the payload; NULL = all ones
+ *   flow_mask (N|1, H, W) sources to ignore (apply_s_flow's `mask`); NULL = all true
+ *   occlude_zero  != 0: sources with |f0|<1e-3 and |f1|<1e-3 are left out and filled back in where
+ *                 nothing landed (utils.py:1190-1203); requires relative != 0
+ *   acc       workspace of N*(C+2)*H*W floats, zero-filled by the call
+ *   out (N,C,H,W); density (N,H,W) NULL ok; warped_mask (N,H,W) = density > 0, NULL ok;
+ *   unocc (N,H,W) = pixels filled back in by the occlusion rule (needed by the adjoint), NULL ok;
+ *   valid (N,H,W) by rule valid_mode, NULL ok. */
+int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
+                    const float *data, int64_t data_bs,
+                    const uint8_t *data_mask, int64_t data_mask_bs,
+                    const uint8_t *flow_mask, int64_t flow_mask_bs,
+                    int occlude_zero, float *acc,
+                    float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
+                    uint8_t *valid, int valid_mode,
+                    int N, int C, int H, int W, void *stream);
+
+/* Adjoint of ofb_splat_s_fwd with respect to the coordinates (hence the flow) and the data.
+ *   out, density, unocc   the forward results (out BEFORE any dtype rounding; unocc NULL = none)
+ *   gout (N,C,H,W); gdensity (N,H,W) NULL = zero
+ *   gcx, gcy       (N,H,W) planes with batch stride gcoord_bs (the two planes of gflow), NULL ok (both)
+ *   gdata          (N,C,H,W), NULL ok */
+int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
+                    const float *data, int64_t data_bs,
+                    const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
+                    const float *out, const float *density, const uint8_t *unocc,
+                    const float *gout, const float *gdensity,
+                    float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                    int N, int C, int H, int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFLIB_B200_H */

@@ -1,0 +1,347 @@
+"""torch.library registration of the sm_100a kernels and their autograd wrappers.
+
+``torch.ops.oflib_b200.*`` are thin launchers over the C ABI (include/oflib_b200.h): they allocate the
+outputs with torch (device memory + caching allocator are torch's job here), resolve batch broadcasting
+into element strides and launch on the current CUDA stream.  CUDA tensors only -- there is no CPU kernel
+registered and no fallback.
+
+Two autograd.Functions give the two primitives of the hot path their hand-written adjoints:
+``warp_t`` (W, reference utils.py:541-555) and ``splat_s`` (S, reference utils.py:1061-1205).  Boolean
+outputs are marked non-differentiable.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _native
+
+VALID_NONE, VALID_GT, VALID_EQ1 = 0, 1, 2
+
+_lib = torch.library.Library("oflib_b200", "DEF")
+_lib.define("flow_stats(Tensor flow, Tensor? mask) -> Tensor")
+_lib.define("warp_t_fwd(Tensor flow, float sign, Tensor? src, Tensor? src_mask, Tensor? flow_mask, "
+            "float add_flow, float thresh, bool want_valid) -> (Tensor, Tensor)")
+_lib.define("warp_t_bwd(Tensor flow, float sign, Tensor src, Tensor gout, float add_flow, "
+            "bool need_gflow, bool need_gsrc) -> (Tensor, Tensor)")
+_lib.define("splat_s_fwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor? data, Tensor? data_mask, "
+            "Tensor? flow_mask, bool occlude_zero, int valid_mode) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+_lib.define("splat_s_bwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor data, Tensor? flow_mask, "
+            "bool occlude_zero, Tensor out, Tensor density, Tensor? unocc, Tensor? gout, Tensor? gdensity, "
+            "bool need_gcoord, bool need_gdata) -> (Tensor, Tensor)")
+
+
+# Optional per-call device timing (bench.py): when PROFILE is a list, every C-ABI call is bracketed by CUDA events
+# recorded on the launching stream and (name, start, end) is appended.  None (default) = no events.
+PROFILE = None
+
+
+def _call(name: str, *args):
+    fn = getattr(_native.lib(), name)
+    if PROFILE is None:
+        _native.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _native.check(fn(*args), name)
+    e1.record()
+    PROFILE.append((name, e0, e1))
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "oflibpytorch_b200: %s is on device '%s'. This library runs its hot path on CUDA (sm_100a) only and "
+            "has no CPU fallback; move the tensors to a CUDA device first." % (what, t.device))
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _maskc(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.bool:
+        t = t.to(torch.bool)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _batch(n: int, *tensors) -> int:
+    for t in tensors:
+        if t is not None:
+            b = t.shape[0]
+            if b != n and b != 1 and n != 1:
+                raise ValueError("oflibpytorch_b200: batch sizes %d and %d cannot be broadcast" % (n, b))
+            n = max(n, b)
+    return n
+
+
+def _bs(t: Optional[torch.Tensor], n: int, per_item: int) -> int:
+    """Batch stride in elements; 0 broadcasts a single item (reference utils.py:527-537)."""
+    if t is None:
+        return 0
+    return 0 if (t.shape[0] == 1 and n > 1) else per_item
+
+
+# ----------------------------------------------------------------------------------------------------
+# raw ops
+# ----------------------------------------------------------------------------------------------------
+
+def _flow_stats(flow: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    require_cuda(flow, "flow")
+    flow = _f32c(flow)
+    mask = _maskc(mask)
+    n, _, h, w = flow.shape
+    if mask is not None and mask.shape[0] != n:
+        mask = mask.expand(n, -1, -1).contiguous()
+    with torch.cuda.device(flow.device):
+        flags = torch.zeros((n,), dtype=torch.int32, device=flow.device)
+        _call("ofb_flow_stats", _p(flow), _p(mask), _p(flags), n, h, w, _stream())
+    return flags
+
+
+def _warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid) -> Tuple[torch.Tensor, torch.Tensor]:
+    require_cuda(flow, "flow")
+    flow = _f32c(flow)
+    src = None if src is None else _f32c(src)
+    src_mask, flow_mask = _maskc(src_mask), _maskc(flow_mask)
+    _, _, h, w = flow.shape
+    c = 0 if src is None else src.shape[1]
+    n = _batch(flow.shape[0], src, src_mask, flow_mask)
+    hw = h * w
+    dev = flow.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
+        valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
+        _call("ofb_warp_t_fwd", 
+            _p(flow), _bs(flow, n, 2 * hw), sign,
+            _p(src) if c else None, _bs(src, n, c * hw),
+            _p(src_mask), _bs(src_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
+            add_flow, thresh, _p(out) if c else None, _p(valid) if want_valid else None,
+            n, c, h, w, _stream())
+    return out, valid
+
+
+def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc) -> Tuple[torch.Tensor, torch.Tensor]:
+    require_cuda(flow, "flow")
+    flow, src, gout = _f32c(flow), _f32c(src), _f32c(gout)
+    n, c, h, w = gout.shape
+    hw = h * w
+    dev = flow.device
+    with torch.cuda.device(dev):
+        gflow = torch.empty((n, 2, h, w) if need_gflow else (0,), dtype=torch.float32, device=dev)
+        gsrc = torch.empty(tuple(src.shape) if need_gsrc else (0,), dtype=torch.float32, device=dev)
+        _call("ofb_warp_t_bwd", 
+            _p(flow), _bs(flow, n, 2 * hw), sign, _p(src), _bs(src, n, c * hw), _p(gout), add_flow,
+            _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None, _bs(src, n, c * hw),
+            n, c, h, w, _stream())
+    return gflow, gsrc
+
+
+def _coord_planes(cx: torch.Tensor, cy: torch.Tensor):
+    """Two (N,H,W) fp32 planes with unit inner strides and a common batch stride (views of one flow tensor
+    qualify, so flow[:, 0], flow[:, 1] are passed without a copy)."""
+    h, w = cx.shape[-2:]
+
+    def ok(t):
+        return t.dtype == torch.float32 and t.stride(-1) == 1 and t.stride(-2) == w
+
+    if not (ok(cx) and ok(cy) and cx.stride(0) == cy.stride(0)):
+        cx, cy = _f32c(cx), _f32c(cy)
+    return cx, cy
+
+
+def _splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask, occlude_zero, valid_mode):
+    require_cuda(cx, "flow")
+    cx, cy = _coord_planes(cx, cy)
+    data = None if data is None else _f32c(data)
+    data_mask, flow_mask = _maskc(data_mask), _maskc(flow_mask)
+    h, w = cx.shape[-2:]
+    hw = h * w
+    c = 0 if data is None else data.shape[1]
+    n = _batch(cx.shape[0], data, data_mask, flow_mask)
+    dev = cx.device
+    want_valid = valid_mode != VALID_NONE
+    with torch.cuda.device(dev):
+        acc = torch.empty((n, c + 2, h, w), dtype=torch.float32, device=dev)
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
+        density = torch.empty((n, h, w), dtype=torch.float32, device=dev)
+        wmask = torch.empty((n, h, w), dtype=torch.bool, device=dev)
+        unocc = torch.empty((n, h, w) if occlude_zero else (0,), dtype=torch.bool, device=dev)
+        valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
+        _call("ofb_splat_s_fwd", 
+            _p(cx), _p(cy), 0 if (cx.shape[0] == 1 and n > 1) else cx.stride(0), int(relative), sign,
+            _p(data) if c else None, _bs(data, n, c * hw),
+            _p(data_mask), _bs(data_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
+            int(occlude_zero), _p(acc), _p(out) if c else None, _p(density), _p(wmask),
+            _p(unocc) if occlude_zero else None, _p(valid) if want_valid else None, valid_mode,
+            n, c, h, w, _stream())
+    return out, density, wmask, unocc, valid
+
+
+def _splat_s_bwd(cx, cy, relative, sign, data, flow_mask, occlude_zero, out, density, unocc, gout, gdensity,
+                 need_gcoord, need_gdata):
+    require_cuda(cx, "flow")
+    cx, cy = _coord_planes(cx, cy)
+    data, out, density = _f32c(data), _f32c(out), _f32c(density)
+    flow_mask = _maskc(flow_mask)
+    n, c, h, w = out.shape
+    hw = h * w
+    dev = cx.device
+    with torch.cuda.device(dev):
+        gout = torch.zeros_like(out) if gout is None else _f32c(gout)
+        gdensity = None if gdensity is None else _f32c(gdensity)
+        gcoord = torch.empty((n, 2, h, w) if need_gcoord else (0,), dtype=torch.float32, device=dev)
+        gdata = torch.empty((n, c, h, w) if need_gdata else (0,), dtype=torch.float32, device=dev)
+        gcx = ctypes.c_void_p(gcoord.data_ptr()) if need_gcoord else None
+        gcy = ctypes.c_void_p(gcoord.data_ptr() + 4 * hw) if need_gcoord else None
+        _call("ofb_splat_s_bwd", 
+            _p(cx), _p(cy), 0 if (cx.shape[0] == 1 and n > 1) else cx.stride(0), int(relative), sign,
+            _p(data), _bs(data, n, c * hw), _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero),
+            _p(out), _p(density), _p(unocc) if (unocc is not None and unocc.numel()) else None,
+            _p(gout), _p(gdensity), gcx, gcy, 2 * hw, _p(gdata) if need_gdata else None,
+            n, c, h, w, _stream())
+    return gcoord, gdata
+
+
+_lib.impl("flow_stats", _flow_stats, "CUDA")
+_lib.impl("warp_t_fwd", _warp_t_fwd, "CUDA")
+_lib.impl("warp_t_bwd", _warp_t_bwd, "CUDA")
+_lib.impl("splat_s_fwd", _splat_s_fwd, "CUDA")
+_lib.impl("splat_s_bwd", _splat_s_bwd, "CUDA")
+
+_ops = torch.ops.oflib_b200
+
+
+# ----------------------------------------------------------------------------------------------------
+# autograd wrappers
+# ----------------------------------------------------------------------------------------------------
+
+def _reduce_to(g: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """Sum a per-item gradient over the batch when the input was a broadcast single item."""
+    if like.shape[0] == 1 and g.shape[0] != 1:
+        g = g.sum(0, keepdim=True)
+    return g
+
+
+class _WarpT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, src, src_mask, flow_mask, sign, add_flow, thresh, want_valid):
+        out, valid = _ops.warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid)
+        ctx.save_for_backward(flow, src)
+        ctx.sign, ctx.add_flow = sign, add_flow
+        ctx.mark_non_differentiable(valid)
+        return out, valid
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, _gvalid):
+        flow, src = ctx.saved_tensors
+        need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gflow = gsrc = None
+        if need_gflow or need_gsrc:
+            gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc)
+            if need_gflow:
+                gflow = _reduce_to(gf, flow)
+            if need_gsrc:
+                gsrc = gs
+        return gflow, gsrc, None, None, None, None, None, None
+
+
+class _SplatS(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cx, cy, data, data_mask, flow_mask, relative, sign, occlude_zero, valid_mode):
+        out, density, wmask, unocc, valid = _ops.splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask,
+                                                             occlude_zero, valid_mode)
+        ctx.save_for_backward(cx, cy, data, flow_mask, out, density, unocc)
+        ctx.relative, ctx.sign, ctx.occlude_zero = relative, sign, occlude_zero
+        ctx.mark_non_differentiable(wmask, valid)
+        return out, density, wmask, valid
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, gdensity, _gw, _gv):
+        cx, cy, data, flow_mask, out, density, unocc = ctx.saved_tensors
+        need_gc = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_gd = ctx.needs_input_grad[2]
+        gcx = gcy = gdata = None
+        if need_gc or need_gd:
+            gcoord, gd = _ops.splat_s_bwd(cx, cy, ctx.relative, ctx.sign, data, flow_mask, ctx.occlude_zero,
+                                          out, density, unocc, gout, gdensity, need_gc, need_gd)
+            if need_gc:
+                gcx = _reduce_to(gcoord[:, 0], cx)
+                gcy = _reduce_to(gcoord[:, 1], cy)
+            if need_gd:
+                gdata = _reduce_to(gd, data)
+        return gcx, gcy, gdata, None, None, None, None, None, None
+
+
+def flow_stats(flow: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-item OFB_STAT_* bits (int32, on the device)."""
+    return _ops.flow_stats(flow.detach(), mask)
+
+
+def warp_t(flow, src, src_mask=None, flow_mask=None, sign=1.0, add_flow=0.0, thresh=0.99999,
+           want_valid=False):
+    """W.  Returns (out, valid); valid is an empty tensor unless want_valid.  src may be None (C = 0)."""
+    if src is None:
+        return _ops.warp_t_fwd(flow.detach(), float(sign), None, src_mask, flow_mask, 0.0, float(thresh), True)
+    return _WarpT.apply(flow, src, src_mask, flow_mask, float(sign), float(add_flow), float(thresh),
+                        bool(want_valid))
+
+
+def splat_flow(flow, data, data_mask=None, flow_mask=None, sign=1.0, occlude_zero=True, valid_mode=VALID_NONE):
+    """S driven by a flow field (N,2,H,W).  Returns (out, density, warped_mask, valid)."""
+    if data is None:
+        f = flow.detach()
+        out, density, wmask, _u, valid = _ops.splat_s_fwd(f[:, 0], f[:, 1], True, float(sign), None, data_mask,
+                                                          flow_mask, bool(occlude_zero), int(valid_mode))
+        return out, density, wmask, valid
+    return _SplatFlow.apply(flow, data, data_mask, flow_mask, float(sign), bool(occlude_zero), int(valid_mode))
+
+
+class _SplatFlow(torch.autograd.Function):
+    """S with the coordinates given as the two planes of one flow tensor (no copies)."""
+
+    @staticmethod
+    def forward(ctx, flow, data, data_mask, flow_mask, sign, occlude_zero, valid_mode):
+        flow = _f32c(flow)
+        out, density, wmask, unocc, valid = _ops.splat_s_fwd(flow[:, 0], flow[:, 1], True, sign, data, data_mask,
+                                                             flow_mask, occlude_zero, valid_mode)
+        ctx.save_for_backward(flow, data, flow_mask, out, density, unocc)
+        ctx.sign, ctx.occlude_zero = sign, occlude_zero
+        ctx.mark_non_differentiable(wmask, valid)
+        return out, density, wmask, valid
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, gdensity, _gw, _gv):
+        flow, data, flow_mask, out, density, unocc = ctx.saved_tensors
+        need_gf, need_gd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gflow = gdata = None
+        if need_gf or need_gd:
+            gcoord, gd = _ops.splat_s_bwd(flow[:, 0], flow[:, 1], True, ctx.sign, data, flow_mask,
+                                          ctx.occlude_zero, out, density, unocc, gout, gdensity, need_gf, need_gd)
+            if need_gf:
+                gflow = _reduce_to(gcoord, flow)
+            if need_gd:
+                gdata = _reduce_to(gd, data)
+        return gflow, gdata, None, None, None, None, None
+
+
+def splat_xy(x, y, data, mask=None):
+    """S with absolute coordinates (grid_from_unstructured_data, utils.py:1061).  Returns (out, density)."""
+    out, density, _w, _v = _SplatS.apply(x, y, data, None, mask, False, 1.0, False, VALID_NONE)
+    return out, density

@@ -1,0 +1,540 @@
+"""The ``Flow`` container and its hot-path methods, API-compatible with the reference's
+``oflibpytorch/flow_class.py`` for: construction and properties (flow_class.py:37-236), arithmetic
+(:450-692), ``pad``/``unpad`` (:715-753), ``apply`` (:755-959), ``switch_ref`` (:1022-1062), ``invert``
+(:1064-1086), ``valid_target``/``valid_source`` (:1088-1172), ``is_zero`` (:1226-1244) and ``combine_with``
+(:1648-1810).
+
+What is different from the reference, by design:
+
+* every hot-path method is a fixed, short sequence of kernel launches: the payload
+  is never concatenated with a float copy of the mask, masks are read and written as bytes by the same kernel
+  that warps the payload, `-vecs` is a kernel argument (sign) rather than a tensor, and `combine_with` mode 3 is
+  ONE kernel;
+* a Flow validates its vectors once (one reduction kernel, one host sync) and remembers the per-item
+  finite/zero flags; results of hot-path methods are built without re-validation (the reference re-runs
+  ``isfinite().all()`` and a mask value scan on every returned Flow, flow_class.py:92,180);
+* CUDA tensors only for the hot-path methods (no CPU fallback); a Flow may hold CPU tensors as a container.
+"""
+import warnings
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as f
+
+from . import _ops
+from ._ops import VALID_EQ1, VALID_GT, VALID_NONE
+from .utils import (STAT_NONFINITE, _is_zero_from_stats, _restore_dtype, _valid_vecs, get_pure_pytorch,
+                    get_valid_device, get_valid_mask, get_valid_padding, get_valid_ref, get_valid_shape)
+
+FlowAlias = 'Flow'
+
+
+class Flow(object):
+    _vecs: torch.Tensor
+    _mask: torch.Tensor
+    _ref: str
+    _device: torch.device
+
+    def __init__(self, flow_vectors: Union[np.ndarray, torch.Tensor], ref: str = None,
+                 mask: Union[np.ndarray, torch.Tensor] = None, device: Union[torch.device, int, str] = None):
+        """Same arguments and validation as the reference constructor (flow_class.py:37-66).
+
+        :param flow_vectors: (2,H,W), (N,2,H,W), (H,W,2) or (N,H,W,2) array or tensor, OpenCV convention
+        :param ref: 't' (default) or 's'
+        :param mask: (H,W) or (N,H,W), True where the vectors are valid; defaults to all True
+        :param device: tensor device; defaults to the device of `flow_vectors`
+        """
+        self._stats = None
+        # If the mask is already a device-resident bool tensor of the right shape, the single validation pass
+        # over the vectors (finite test, utils.py:98) also yields the mask-aware zero flags (flow_class.py:1243).
+        self._mask_hint = None
+        if isinstance(mask, torch.Tensor) and mask.dtype == torch.bool and mask.is_cuda and \
+                isinstance(flow_vectors, torch.Tensor) and flow_vectors.device == mask.device and \
+                flow_vectors.dim() == 4 and flow_vectors.shape[1] == 2 and \
+                tuple(mask.shape) == (flow_vectors.shape[0],) + tuple(flow_vectors.shape[2:]):
+            self._mask_hint = mask
+        self.vecs = flow_vectors
+        self.ref = ref
+        self.mask = mask
+        self.device = device
+        self._mask_hint = None
+
+    # ------------------------------------------------------------------ construction without re-validation
+    @classmethod
+    def _make(cls, vecs: torch.Tensor, ref: str, mask: torch.Tensor) -> FlowAlias:
+        """Internal: wrap kernel outputs (already N-2-H-W fp32 / N-H-W bool on one device)."""
+        obj = cls.__new__(cls)
+        obj._vecs, obj._ref, obj._mask, obj._device, obj._stats = vecs, ref, mask, vecs.device, None
+        return obj
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def vecs(self) -> torch.Tensor:
+        return self._vecs
+
+    @vecs.setter
+    def vecs(self, input_vecs):
+        hint = getattr(self, '_mask_hint', None)
+        v, stats = _valid_vecs(input_vecs, error_string="Error setting flow vectors: ", want_stats=True, mask=hint)
+        self._vecs = v
+        # without a mask hint the flags of this pass are unmasked; the masked bits are only trusted once a
+        # mask-aware pass ran
+        self._stats = None
+        self._stats_unmasked = None if hint is not None else stats
+        self._stats_hinted = stats if hint is not None else None
+
+    @property
+    def vecs_numpy(self) -> np.ndarray:
+        return np.moveaxis(self._vecs.detach().cpu().numpy(), 1, -1)
+
+    @property
+    def ref(self) -> str:
+        return self._ref
+
+    @ref.setter
+    def ref(self, input_ref: str = None):
+        self._ref = get_valid_ref(input_ref)
+
+    @property
+    def mask(self) -> torch.Tensor:
+        return self._mask
+
+    @mask.setter
+    def mask(self, input_mask=None):
+        if input_mask is None:
+            self._mask = torch.ones(self.shape, dtype=torch.bool, device=self._vecs.device)
+            if getattr(self, '_stats_unmasked', None) is not None:
+                # all-true mask: masked bits == unmasked bits
+                self._stats = [fl | ((fl & 2) << 2) | ((fl & 4) << 2) for fl in self._stats_unmasked]
+        else:
+            m = get_valid_mask(input_mask, desired_shape=self.shape, error_string="Error setting flow mask: ")
+            self._mask = m.to(self._vecs.device)
+            hinted = getattr(self, '_stats_hinted', None)
+            self._stats = hinted if (hinted is not None and input_mask is getattr(self, '_mask_hint', None)) else None
+            self._stats_hinted = None
+
+    @property
+    def mask_numpy(self) -> np.ndarray:
+        return self._mask.detach().cpu().numpy()
+
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    @device.setter
+    def device(self, input_device=None):
+        device = self._vecs.device if input_device is None else get_valid_device(input_device)
+        self._device = device
+        self._vecs = self._vecs.to(device)
+        self._mask = self._mask.to(device)
+
+    @property
+    def shape(self) -> tuple:
+        return (self._vecs.shape[0],) + tuple(self._vecs.shape[2:])
+
+    @classmethod
+    def zero(cls, shape, ref: str = None, mask=None, device=None) -> FlowAlias:
+        """reference flow_class.py:238-260"""
+        s = get_valid_shape(shape)
+        dev = get_valid_device(device)
+        return cls(torch.zeros(s[0], 2, s[1], s[2], device=dev), ref, mask, dev)
+
+    def copy(self) -> FlowAlias:
+        return Flow(self._vecs, self._ref, self._mask, self._device)
+
+    def to_device(self, device) -> FlowAlias:
+        device = get_valid_device(device)
+        return Flow(self._vecs.to(device), self._ref, self._mask.to(device), device)
+
+    def __str__(self) -> str:
+        return "Flow object, reference {}, batch size {}, shape {}*{}, device {}; ".format(
+            self._ref, *self.shape, self._device) + self.__repr__()
+
+    def select(self, item: int = None) -> FlowAlias:
+        """reference flow_class.py:413-430"""
+        if item is None:
+            return self
+        if not isinstance(item, int):
+            raise TypeError("Error selecting from flow object: item needs to be an integer")
+        try:
+            return Flow(self._vecs[item], self._ref, self._mask[item], self._device)
+        except IndexError:
+            raise IndexError("Error selecting from flow object: item {} out of bounds for flow with batch size {}"
+                             .format(item, self.shape[0]))
+
+    def __getitem__(self, item) -> FlowAlias:
+        """Spatial slicing like a (H,W,...) tensor (reference flow_class.py:432-448)."""
+        vecs = self._vecs.permute(2, 3, 0, 1).__getitem__(item).permute(2, 3, 0, 1)
+        mask = self._mask.permute(1, 2, 0).__getitem__(item).permute(2, 0, 1)
+        return Flow(vecs, self._ref, mask, self._device)
+
+    # ------------------------------------------------------------------ arithmetic (flow_class.py:450-692)
+    def _other_operand(self, other, verb: str, noun: str, err_a: str):
+        if isinstance(other, (np.ndarray, torch.Tensor)):
+            ov = _valid_vecs(other, desired_shape=self.shape, error_string="Error adding to flow: ")
+            om = None
+        elif isinstance(other, Flow):
+            ov, om = other._vecs, other._mask
+        else:
+            raise TypeError("Error {} flow: {} is not a flow object, numpy array, or torch tensor".format(verb, noun))
+        if self.shape[0] != ov.shape[0] and self.shape[0] != 1 and ov.shape[0] != 1:
+            raise ValueError(err_a)
+        return ov.to(self._device), (None if om is None else om.to(self._device))
+
+    def __add__(self, other) -> FlowAlias:
+        ov, om = self._other_operand(other, "adding to", "Addend",
+                                     "Error adding to flow: Augend and addend batch dimensions don't match, "
+                                     "and neither is 1")
+        if self.shape[1:] != tuple(ov.shape[2:]):
+            raise ValueError("Error adding to flow: Augend and addend flow objects are not the same shape")
+        return Flow._make(self._vecs + ov, self._ref, self._mask if om is None else (self._mask & om))
+
+    def __sub__(self, other) -> FlowAlias:
+        ov, om = self._other_operand(other, "subtracting from", "Subtrahend",
+                                     "Error subtracting from flow: Minuend and subtrahend batch dimensions don't "
+                                     "match, and neither is 1")
+        if self.shape[1:] != tuple(ov.shape[2:]):
+            raise ValueError("Error subtracting from flow: Minuend and subtrahend flow objects are not the same shape")
+        return Flow._make(self._vecs - ov, self._ref, self._mask if om is None else (self._mask & om))
+
+    def _scalar_like(self, other, verb: str, noun: str):
+        """Shared operand handling of __mul__/__truediv__/__pow__ (flow_class.py:533-678)."""
+        try:
+            return float(other)
+        except (TypeError, ValueError):
+            pass
+        if isinstance(other, list):
+            if len(other) != 2:
+                raise ValueError("Error {} flow: {} list not length 2".format(verb, noun))
+            other = torch.tensor(other)
+        elif isinstance(other, np.ndarray):
+            other = torch.tensor(other)
+        if not isinstance(other, torch.Tensor):
+            raise TypeError("Error {} flow: {} cannot be converted to float, or isn't a list, numpy array, "
+                            "or torch tensor".format(verb, noun))
+        hw = tuple(self.shape[1:])
+        if other.dim() == 1 and other.shape[0] == 2:
+            other = other.view(1, 2, 1, 1)
+        elif other.dim() == 2 and tuple(other.shape) == hw:
+            other = other[None, None]
+        elif other.dim() == 3 and tuple(other.shape) == (2,) + hw:
+            other = other[None]
+        elif other.dim() == 3 and tuple(other.shape) == hw + (2,):
+            other = other.permute(2, 0, 1)[None]
+        elif other.dim() == 4 and tuple(other.shape[2:]) == hw and other.shape[1] == 2 and \
+                (self.shape[0] == 1 or other.shape[0] == 1 or self.shape[0] == other.shape[0]):
+            pass
+        else:
+            raise ValueError("Error {} flow: {} array or tensor needs to be of size 2, of the shape of the flow "
+                             "object (H-W), or 2-H-W or H-W-2, or N-2-H-W".format(verb, noun))
+        return other.to(self._device)
+
+    def _with_vecs(self, v: torch.Tensor) -> FlowAlias:
+        m = self._mask if v.shape[0] == self.shape[0] else self._mask.repeat(v.shape[0], 1, 1)
+        return Flow(v, self._ref, m, self._device)
+
+    def __mul__(self, other) -> FlowAlias:
+        return self._with_vecs(self._vecs * self._scalar_like(other, "multiplying", "Multiplier"))
+
+    def __truediv__(self, other) -> FlowAlias:
+        return self._with_vecs(self._vecs / self._scalar_like(other, "dividing", "Divisor"))
+
+    def __pow__(self, other) -> FlowAlias:
+        return self._with_vecs(self._vecs ** self._scalar_like(other, "exponentiating", "Exponent"))
+
+    def __neg__(self) -> FlowAlias:
+        out = Flow._make(self._vecs * -1.0, self._ref, self._mask)
+        out._stats = self._stats        # |v| tests are sign-symmetric
+        return out
+
+    # ------------------------------------------------------------------ pad / unpad (flow_class.py:715-753)
+    def pad(self, padding: list = None, mode: str = None) -> FlowAlias:
+        mode = 'constant' if mode is None else mode
+        if mode not in ['constant', 'reflect', 'replicate']:
+            raise ValueError("Error padding flow: Mode should be one of "
+                             "'constant', 'reflect', or 'replicate', but instead got '{}'".format(mode))
+        padding = get_valid_padding(padding, "Error padding flow: ")
+        pad4 = (padding[2], padding[3], padding[0], padding[1])
+        vecs = f.pad(self._vecs, pad4, mode=mode)
+        mask = f.pad(self._mask.unsqueeze(1), pad4).squeeze(1)
+        return Flow._make(vecs.contiguous(), self._ref, mask.contiguous())
+
+    def unpad(self, padding: list = None) -> FlowAlias:
+        padding = get_valid_padding(padding, "Error padding flow: ")
+        h, w = self.shape[1:3]
+        if sum(padding[0:2]) > h - 1 or sum(padding[2:4]) > w - 1:
+            raise ValueError("Error unpadding flow: one or more dimensions cut to zero or less")
+        return self[padding[0]:h - padding[1], padding[2]:w - padding[3]]
+
+    # ------------------------------------------------------------------ zero tests
+    def _get_stats(self) -> List[int]:
+        """Per-item OFB_STAT_* flags of (vecs, mask): one kernel, one sync, cached."""
+        if self._stats is None:
+            _ops.require_cuda(self._vecs, "flow")
+            self._stats = _ops.flow_stats(self._vecs, self._mask).tolist()
+        return self._stats
+
+    def is_zero(self, thresholded: bool = None, masked: bool = None) -> torch.Tensor:
+        """reference flow_class.py:1226-1244 (+ utils.py:919-938)"""
+        masked = True if masked is None else masked
+        if not isinstance(masked, bool):
+            raise TypeError("Error checking whether flow is zero: Masked needs to be a boolean")
+        thresholded = True if thresholded is None else thresholded
+        if not isinstance(thresholded, bool):
+            raise TypeError("Error checking whether flow is zero: Thresholded needs to be a boolean")
+        z = _is_zero_from_stats(self._get_stats(), thresholded, masked)
+        return torch.tensor(z, dtype=torch.bool, device=self._device)
+
+    def _all_zero(self, thresholded: bool, masked: bool) -> bool:
+        return all(_is_zero_from_stats(self._get_stats(), thresholded, masked))
+
+    # ------------------------------------------------------------------ the warp itself
+    def _warp(self, payload: torch.Tensor, payload_mask: Optional[torch.Tensor], need_valid: bool,
+              consider_mask: bool, sign: float = 1.0, flow_mask_and: bool = True
+              ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """apply_flow(sign*vecs, [payload | payload_mask], ref, mask) followed by the 0.99999 threshold of
+        Flow.apply, as one launch sequence.  For 't' the valid bit is ANDed with self.mask when `flow_mask_and`;
+        for 's' `payload_mask` must already contain the AND with self.mask (flow_class.py:880-895).
+        Includes the zero-flow early-out of apply_flow (utils.py:497-498)."""
+        if self._all_zero(thresholded=True, masked=False):
+            n = max(payload.shape[0], self.shape[0], 1 if payload_mask is None else payload_mask.shape[0])
+            out = payload
+            valid = None
+            if need_valid:
+                valid = payload_mask if payload_mask is not None else \
+                    torch.ones((n,) + tuple(payload.shape[2:]), dtype=torch.bool, device=payload.device)
+                if valid.shape[0] != n:
+                    valid = valid.expand(n, -1, -1)
+                if out.shape[0] != n:
+                    out = out.expand(n, -1, -1, -1)
+                if self._ref == 't' and flow_mask_and:
+                    valid = valid & self._mask
+            return out, valid
+        if self._ref == 't':
+            out, valid = _ops.warp_t(self._vecs, payload, payload_mask,
+                                     self._mask if (need_valid and flow_mask_and) else None,
+                                     sign=sign, thresh=0.99999, want_valid=need_valid)
+        else:
+            out, _d, _w, valid = _ops.splat_flow(self._vecs, payload, payload_mask,
+                                                 self._mask if consider_mask else None, sign=sign,
+                                                 occlude_zero=True, valid_mode=VALID_GT if need_valid else VALID_NONE)
+        return out, (valid if need_valid else None)
+
+    def apply(self, target, target_mask: torch.Tensor = None, return_valid_area: bool = None,
+              consider_mask: bool = None, padding: list = None, cut: bool = None):
+        """Apply the flow to a tensor or to another Flow (reference flow_class.py:755-959; same arguments,
+        return values and exceptions).  Differentiable w.r.t. the flow vectors and a tensor target."""
+        return_valid_area = False if return_valid_area is None else return_valid_area
+        if not isinstance(return_valid_area, bool):
+            raise TypeError("Error applying flow: Return_valid_area needs to be a boolean")
+        consider_mask = True if consider_mask is None else consider_mask
+        if not isinstance(consider_mask, bool):
+            raise TypeError("Error applying flow: Consider_mask needs to be a boolean")
+        cut = True if cut is None else cut
+        if not isinstance(cut, bool):
+            raise TypeError("Error applying flow: Cut needs to be a boolean")
+        if padding is not None:
+            padding = get_valid_padding(padding, "Error applying flow: ")
+            if self.shape[1] + padding[0] + padding[1] != target.shape[-2] or \
+                    self.shape[2] + padding[2] + padding[3] != target.shape[-1]:
+                raise ValueError("Error applying flow: Padding values do not match flow and target shape difference")
+
+        return_dtype = torch.float
+        return_2d = return_3d = False
+        if isinstance(target, Flow):
+            return_flow = True
+            t = target._vecs.to(self._device)
+            mask = target._mask.to(self._device)
+        elif isinstance(target, torch.Tensor):
+            return_flow = False
+            if target.dim() == 4:
+                t = target
+            elif target.dim() == 3:
+                t, return_3d = target.unsqueeze(0), True
+            elif target.dim() == 2:
+                t, return_2d = target.unsqueeze(0).unsqueeze(0), True
+            else:
+                raise ValueError("Error applying flow: Target needs to have the shape H-W (2 dimensions)"
+                                 ", C-H-W (3 dimensions), or N-C-H-W (4 dimensions)")
+            t = t.to(torch.float).to(self._device)
+            t_shape = (t.shape[0],) + tuple(t.shape[2:])
+            mask = None                                             # all true, never materialised
+            if target_mask is not None:
+                if not isinstance(target_mask, torch.Tensor):
+                    raise TypeError("Error applying flow: Target_mask needs to be a torch tensor")
+                if target_mask.dim() == 2:
+                    target_mask = target_mask.unsqueeze(0)
+                if tuple(target_mask.shape) != t_shape:
+                    raise ValueError("Error applying flow: Target_mask needs to match the target shape")
+                if target_mask.dtype != torch.bool:
+                    raise TypeError("Error applying flow: Target_mask needs to have dtype 'bool'")
+                if not return_valid_area:
+                    warnings.warn("Warning applying flow: a mask is passed, but return_valid_area is False - so the "
+                                  "mask passed will not affect the output, but possibly make the function slower.")
+                mask = target_mask.to(self._device)
+            return_dtype = target.dtype
+        else:
+            raise TypeError("Error applying flow: Target needs to be either a flow object or a torch tensor")
+        if padding is None and tuple(target.shape[-2:]) != tuple(self.shape[-2:]):
+            raise ValueError("Error applying flow: Flow and target have to have the same shape")
+
+        need_valid = return_flow or return_valid_area
+        flow = self
+        top = left = 0
+        if padding is not None:                                     # flow_class.py:905-914
+            flow = self.pad(padding, mode='constant' if self._ref == 't' else 'replicate')
+            top, left = padding[0], padding[2]
+        fh, fw = self.shape[1], self.shape[2]
+
+        payload_mask = mask
+        if need_valid and self._ref == 's':                         # flow_class.py:880-895
+            if padding is not None:
+                # target mask ANDed with the flow mask inside the flow window, False outside (functional
+                # version of the reference's in-place loop; the caller's mask is left untouched)
+                base = mask if mask is not None else torch.ones((t.shape[0],) + tuple(t.shape[2:]), dtype=torch.bool,
+                                                                device=self._device)
+                n = max(base.shape[0], self.shape[0])
+                pm = torch.zeros((n,) + tuple(base.shape[1:]), dtype=torch.bool, device=self._device)
+                pm[:, top:top + fh, left:left + fw] = base[:, top:top + fh, left:left + fw] & self._mask
+                payload_mask = pm
+            else:
+                payload_mask = self._mask if mask is None else (mask & self._mask)
+
+        uncut = padding is not None and not cut
+        warped, valid = flow._warp(t, payload_mask if need_valid else None, need_valid, consider_mask,
+                                   flow_mask_and=not (padding is not None))
+        if padding is not None and cut:                             # flow_class.py:917-918
+            warped = warped[..., top:top + fh, left:left + fw]
+            if valid is not None:
+                valid = valid[..., top:top + fh, left:left + fw]
+        if need_valid and self._ref == 't' and padding is not None:  # flow_class.py:924-934
+            if uncut:
+                full = torch.zeros_like(valid)
+                full[:, top:top + fh, left:left + fw] = valid[:, top:top + fh, left:left + fw] & self._mask
+                valid = full
+            else:
+                valid = valid & self._mask
+
+        if return_flow:
+            return Flow._make(warped[:, :2].contiguous(), target._ref, valid.contiguous())
+        if not return_dtype.is_floating_point:                      # flow_class.py:943-949
+            warped = torch.round(warped.float())
+            if return_dtype == torch.uint8:
+                warped = torch.clamp(warped, 0, 255)
+            if not get_pure_pytorch():
+                warped = warped.to(return_dtype)
+        else:
+            warped = warped.to(return_dtype)
+        if return_2d and warped.shape[0] == 1:
+            warped = warped.squeeze(0).squeeze(0)
+        if return_3d and warped.shape[0] == 1:
+            warped = warped.squeeze(0)
+        if return_valid_area:
+            return warped, valid
+        return warped
+
+    # ------------------------------------------------------------------ ref switching and inversion
+    def switch_ref(self, mode: str = None) -> FlowAlias:
+        """reference flow_class.py:1022-1062.  'valid' mode is ONE splat whose payload is the flow itself:
+        s->t: S(v, [v|m], m);  t->s: S(-v, [v|m], m)  (SURVEY.md section 3.4)."""
+        mode = 'valid' if mode is None else mode
+        other = 't' if self._ref == 's' else 's'
+        if mode == 'invalid':
+            return Flow._make(self._vecs, other, self._mask)
+        if mode != 'valid':
+            raise ValueError("Error switching flow reference: Mode not recognised, should be 'valid' or 'invalid'")
+        if self._all_zero(thresholded=False, masked=True):
+            return Flow._make(self._vecs, other, self._mask)
+        sign = 1.0 if self._ref == 's' else -1.0
+        return self._splat_self(self._vecs, sign, other)
+
+    def _splat_self(self, payload: torch.Tensor, sign: float, out_ref: str) -> FlowAlias:
+        """S(sign*v, [payload | m], m) with apply_flow's early-out (thresholded, unmasked; utils.py:497)."""
+        if self._all_zero(thresholded=True, masked=False):
+            return Flow._make(payload, out_ref, self._mask)
+        out, _d, _w, valid = _ops.splat_flow(self._vecs, payload, self._mask, self._mask, sign=sign,
+                                             occlude_zero=True, valid_mode=VALID_GT)
+        return Flow._make(out, out_ref, valid)
+
+    def invert(self, ref: str = None) -> FlowAlias:
+        """reference flow_class.py:1064-1086"""
+        ref = self._ref if ref is None else get_valid_ref(ref)
+        if ref != self._ref:
+            return -Flow._make(self._vecs, ref, self._mask)          # flow_class.py:1081,1084
+        if self._ref == 's':
+            return self._splat_self(-self._vecs, 1.0, 's')           # self.apply(-self), :1079
+        # 't' -> 't': Flow(-v,'s',m).switch_ref()  (:1086) = S(-v, [-v|m], m) relabelled 't'
+        if self._all_zero(thresholded=False, masked=True):
+            return Flow._make(-self._vecs, 't', self._mask)
+        return self._splat_self(-self._vecs, -1.0, 't')
+
+    # ------------------------------------------------------------------ valid areas (flow_class.py:1088-1172)
+    def _valid_area(self, sign: float, splat: bool, consider_mask: bool) -> torch.Tensor:
+        if self._all_zero(thresholded=True, masked=False):           # apply_flow's early-out returns its input
+            return self._mask.clone() if splat else self._mask.clone()
+        if splat:
+            _o, _d, _w, valid = _ops.splat_flow(self._vecs, None, self._mask, self._mask if consider_mask else None,
+                                                sign=sign, occlude_zero=True, valid_mode=VALID_EQ1)
+            return valid
+        _o, valid = _ops.warp_t(self._vecs, None, None, self._mask, sign=sign, thresh=0.9999, want_valid=True)
+        return valid
+
+    def valid_target(self, consider_mask: bool = None) -> torch.Tensor:
+        consider_mask = True if consider_mask is None else consider_mask
+        if not isinstance(consider_mask, bool):
+            raise TypeError("Error applying flow: Consider_mask needs to be a boolean")
+        return self._valid_area(1.0, self._ref == 's', consider_mask)
+
+    def valid_source(self, consider_mask: bool = None) -> torch.Tensor:
+        consider_mask = True if consider_mask is None else consider_mask
+        if not isinstance(consider_mask, bool):
+            raise TypeError("Error applying flow: Consider_mask needs to be a boolean")
+        return self._valid_area(-1.0, self._ref == 't', consider_mask)
+
+    # ------------------------------------------------------------------ composition (flow_class.py:1648-1810)
+    def combine_with(self, flow: FlowAlias, mode: int, thresholded: bool = None) -> FlowAlias:
+        """flow_1 (+) flow_2 = flow_3, solved for the flow named by `mode` (reference flow_class.py:1648-1810).
+        Mode 3 is a single fused kernel: warp + add + mask AND."""
+        if not isinstance(flow, Flow):
+            raise TypeError("Error combining flows: Flow need to be of type 'Flow'")
+        if self.shape != flow.shape:
+            raise ValueError("Error combining flows: Flow fields need to have the same shape, including batch size")
+        if self.ref != flow.ref:
+            raise ValueError("Error combining flows: Flow fields need to have the same reference")
+        if self._device != flow._device:
+            flow = flow.to_device(self._device)
+        if mode not in [1, 2, 3]:
+            raise ValueError("Error combining flows: Mode needs to be 1, 2 or 3")
+        thresholded = False if thresholded is None else thresholded
+        if not isinstance(thresholded, bool):
+            raise TypeError("Error combining flows: Thresholded needs to be a boolean")
+
+        if self._all_zero(thresholded, masked=True):                 # flow_class.py:1729-1744
+            return flow
+        if flow._all_zero(thresholded, masked=True):
+            return self if mode == 3 else self.invert()
+
+        s = self._ref == 's'
+        if mode == 3:
+            if s:   # self + self.invert('t').apply(flow)  = v1 + W(-v1, [v2|m2]),  mask theta & m1
+                return self._fused_warp_add(flow, sign=-1.0)
+            # flow + flow.apply(self) = v2 + W(v2, [v1|m1]),  mask theta & m2
+            return flow._fused_warp_add(self, sign=1.0)
+        if mode == 2:
+            if s:
+                return self.apply(flow - self)                       # flow_class.py:1768
+            return flow - flow.apply(self.invert().apply(self))      # flow_class.py:1773
+        if s:                                                        # mode 1, flow_class.py:1759-1760
+            flow_inv_t = flow.invert('t')
+            return flow - (flow_inv_t + flow_inv_t.apply(self.switch_ref())).apply(self)
+        return self.invert().apply(flow - self)                      # flow_class.py:1763
+
+    def _fused_warp_add(self, payload: FlowAlias, sign: float) -> FlowAlias:
+        """v_self + W(sign*v_self, [v_payload | m_payload]) with mask (theta(mask channel) & m_self).
+        Restates  self + Flow(sign*v_self,'t',m_self).apply(payload)  including apply_flow's early-out."""
+        if self._all_zero(thresholded=True, masked=False):
+            return Flow._make(self._vecs + payload._vecs, self._ref, payload._mask & self._mask)
+        out, valid = _ops.warp_t(self._vecs, payload._vecs, payload._mask, self._mask, sign=sign, add_flow=1.0,
+                                 thresh=0.99999, want_valid=True)
+        return Flow._make(out, self._ref, valid)

@@ -1,0 +1,328 @@
+"""Functional layer of the hot path: same names, arguments, return conventions and error behaviour as the
+reference's ``oflibpytorch/utils.py``, served by the sm_100a kernels.
+
+Reference map (``/root/reference/src/oflibpytorch/utils.py``):
+
+=============================  ========================  =============================================
+here                           reference                 what changed
+=============================  ========================  =============================================
+get_valid_* / validation       utils.py:72-232           same checks and messages; the finite test and
+                                                         the zero tests are ONE kernel pass + ONE sync
+apply_flow                     utils.py:469-620          't': one fused gather kernel; 's': splat kernels
+get_flow_endpoints             utils.py:1045-1058        kept for API parity (the kernels fuse it)
+grid_from_unstructured_data    utils.py:1061-1154        accumulate + normalise kernels, no index tensors
+apply_s_flow                   utils.py:1157-1205        occlusion rule and fill fused into the splat
+threshold_vectors/is_zero_flow utils.py:623-643,919-938  is_zero_flow is a flag reduction
+=============================  ========================  =============================================
+
+CUDA tensors only.  CPU inputs are validated like the reference validates them (same exceptions) and then
+rejected with a RuntimeError: there is deliberately no CPU path in this package.
+"""
+from typing import Any, List, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _ops
+from ._ops import VALID_EQ1, VALID_GT, VALID_NONE  # noqa: F401
+
+DEFAULT_THRESHOLD = 1e-3
+PURE_PYTORCH = True
+
+STAT_NONFINITE, STAT_NONZERO, STAT_NONZERO_T, STAT_NONZERO_M, STAT_NONZERO_TM = 1, 2, 4, 8, 16
+
+
+# ----------------------------------------------------------------------------------------------------
+# toolbox-wide switch (reference utils.py:24-69).  Only the differentiable splat mode exists here.
+# ----------------------------------------------------------------------------------------------------
+
+def get_pure_pytorch() -> bool:
+    return PURE_PYTORCH
+
+
+def set_pure_pytorch(warn: bool = None):
+    global PURE_PYTORCH
+    PURE_PYTORCH = True
+    if warn:
+        print("Pure Pytorch mode set: no use of scipy.interpolate.griddata. Differentiable, significantly faster, "
+              "but more approximate")
+
+
+def unset_pure_pytorch(warn: bool = None):
+    raise NotImplementedError(
+        "oflibpytorch_b200 implements the PURE_PYTORCH=True path only (the scipy.interpolate.griddata branch of the "
+        "reference is CPU-only, non-differentiable and out of scope); use the reference package for it.")
+
+
+# ----------------------------------------------------------------------------------------------------
+# validation (reference utils.py:72-232) -- the error contract of the boundary
+# ----------------------------------------------------------------------------------------------------
+
+def _valid_vecs(vecs: Any, desired_shape=None, error_string: str = None, want_stats: bool = False,
+                mask: torch.Tensor = None):
+    """get_valid_vecs plus, optionally, the host copy of the per-item OFB_STAT_* flags obtained in the same
+    pass that checks for NaN/Inf (so that later zero-flow questions cost nothing)."""
+    error_string = '' if error_string is None else error_string
+    if not isinstance(vecs, (np.ndarray, torch.Tensor)):
+        raise TypeError(error_string + "Input is not a numpy array or a torch tensor")
+    ndim = len(vecs.shape)
+    if ndim != 3 and ndim != 4:
+        raise ValueError(error_string + "Input has {} dimensions, should be 3 or 4".format(ndim))
+    if isinstance(vecs, np.ndarray):
+        vecs = torch.tensor(vecs, dtype=torch.float, device='cpu')
+    if ndim == 3:
+        vecs = vecs.unsqueeze(0)
+    if vecs.shape[1] != 2:
+        if vecs.shape[3] == 2:
+            vecs = vecs.permute(0, 3, 1, 2)
+        else:
+            raise ValueError(error_string + "Input needs to be shape (N-)H-W-2 or (N-)2-H-W")
+    stats = None
+    if vecs.is_cuda:
+        v32 = vecs.float().contiguous()
+        flags = _ops.flow_stats(v32, mask).tolist()          # the one sync of the call
+        if any(f & STAT_NONFINITE for f in flags):
+            raise ValueError(error_string + "Input contains NaN, Inf or -Inf values")
+        stats = flags
+        vecs = v32
+    else:
+        if not torch.isfinite(vecs).all():
+            raise ValueError(error_string + "Input contains NaN, Inf or -Inf values")
+        vecs = vecs.float()
+    if desired_shape is not None:
+        d = get_valid_shape(desired_shape)
+        if vecs.shape[0] != d[0] or vecs.shape[2] != d[1] or vecs.shape[3] != d[2]:
+            raise ValueError(error_string + "Input shape does not match the desired shape")
+    return (vecs, stats) if want_stats else vecs
+
+
+def get_valid_vecs(vecs: Any, desired_shape: Union[tuple, list] = None, error_string: str = None) -> torch.Tensor:
+    """Checks array or tensor input and returns an N-2-H-W float tensor (reference utils.py:72-118)."""
+    return _valid_vecs(vecs, desired_shape, error_string)
+
+
+def get_valid_shape(shape: Any) -> tuple:
+    """reference utils.py:121-131"""
+    if not isinstance(shape, (list, tuple)):
+        raise TypeError("Error creating flow from matrix: Dims need to be a list or a tuple")
+    if len(shape) not in (2, 3):
+        raise ValueError("Error creating flow from matrix: Dims need to be a list or a tuple of length 2 or 3")
+    if any((item <= 0 or not isinstance(item, int)) for item in shape):
+        raise ValueError("Error creating flow from matrix: Dims need to be a list or a tuple of integers above zero")
+    return ((1,) + tuple(shape)) if len(shape) == 2 else tuple(shape)
+
+
+def get_valid_ref(ref: Any) -> str:
+    """reference utils.py:134-148"""
+    if ref is None:
+        return 't'
+    if not isinstance(ref, str):
+        raise TypeError("Error setting flow reference: Input is not a string")
+    if ref not in ('s', 't'):
+        raise ValueError("Error setting flow reference: Input is not 's' or 't', but {}".format(ref))
+    return ref
+
+
+def get_valid_mask(mask: Any, desired_shape: Union[tuple, list] = None, error_string: str = None) -> torch.Tensor:
+    """reference utils.py:151-186.  A torch.bool input cannot hold anything but 0/1, so its value check is
+    skipped (no kernel, no sync)."""
+    error_string = '' if error_string is None else error_string
+    if not isinstance(mask, (np.ndarray, torch.Tensor)):
+        raise TypeError(error_string + "Input is not a numpy array or a torch tensor")
+    ndim = len(mask.shape)
+    if ndim != 2 and ndim != 3:
+        raise ValueError(error_string + "Input has {} dimensions, should be 2 or 3".format(ndim))
+    if isinstance(mask, np.ndarray):
+        mask = torch.tensor(mask)
+    if mask.dtype != torch.bool and bool(((mask != 0) & (mask != 1)).any()):
+        raise ValueError(error_string + "Values must be 0 or 1")
+    if ndim == 2:
+        mask = mask.unsqueeze(0)
+    if desired_shape is not None:
+        if tuple(mask.shape) != get_valid_shape(desired_shape):
+            raise ValueError(error_string + "Input shape does not match the desired shape")
+    return mask.to(torch.bool)
+
+
+def get_valid_device(device: Any) -> torch.device:
+    """reference utils.py:189-212"""
+    if device is None:
+        device = torch.device('cpu')
+    elif not isinstance(device, torch.device):
+        try:
+            device = torch.device(device)
+        except RuntimeError:
+            raise ValueError("Error setting tensor device: Input needs to be a torch.device, or valid input to "
+                             "torch.device(). Instead found {}".format(device))
+    if device.type == 'cuda':
+        if not torch.cuda.is_available():
+            raise ValueError("Error setting tensor device: Input is 'cuda', but cuda is not available")
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+    return device
+
+
+def get_valid_padding(padding: Any, error_string: str = None) -> list:
+    """reference utils.py:215-232"""
+    error_string = '' if error_string is None else error_string
+    if not isinstance(padding, (list, tuple)):
+        raise TypeError(error_string + "Padding needs to be a list [top, bot, left, right]")
+    if len(padding) != 4:
+        raise ValueError(error_string + "Padding list needs to be a list of length 4 [top, bot, left, right]")
+    if not all(isinstance(item, int) for item in padding):
+        raise ValueError(error_string + "Padding list [top, bot, left, right] items need to be integers")
+    if not all(item >= 0 for item in padding):
+        raise ValueError(error_string + "Padding list [top, bot, left, right] items need to be 0 or larger")
+    return padding
+
+
+def move_axis(input_tensor: torch.Tensor, source: int, destination: int) -> torch.Tensor:
+    """np.moveaxis for tensors (reference utils.py:235-252)."""
+    return torch.movedim(input_tensor, source, destination)
+
+
+def to_numpy(tensor: torch.Tensor, switch_channels: bool = None) -> np.ndarray:
+    """reference utils.py:255-273"""
+    arr = tensor.detach().cpu().numpy()
+    return np.moveaxis(arr, 1, -1) if switch_channels else arr
+
+
+def normalise_coords(coords: torch.Tensor, shape: Union[tuple, list]) -> torch.Tensor:
+    """Pixel coordinates (x, y) -> [-1, 1] (reference utils.py:445-466).  Kept for API parity; the warp kernel
+    evaluates the same three fp32 operations (x2, /(size-1), -1) in registers."""
+    if len(shape) != 2:
+        raise ValueError("Error normalising coords: Given shape needs to be list or tuple of length 2")
+    out = coords.float() * 2
+    out[..., 0] /= (shape[1] - 1)
+    out[..., 1] /= (shape[0] - 1)
+    out -= 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# zero-flow helpers (reference utils.py:623-643, 919-938)
+# ----------------------------------------------------------------------------------------------------
+
+def threshold_vectors(vecs: torch.Tensor, threshold: Union[float, int] = None, use_mag: bool = None) -> torch.Tensor:
+    """reference utils.py:623-643 (elementwise; differentiable).  The kernels never materialise this tensor:
+    they evaluate the predicate |v| < 1e-3 per component in registers."""
+    threshold = DEFAULT_THRESHOLD if threshold is None else threshold
+    if use_mag:
+        small = (torch.norm(vecs, dim=1, keepdim=True) < threshold).expand(-1, 2, -1, -1)
+    else:
+        small = (vecs < threshold) & (vecs > -threshold)
+    return torch.where(small, torch.zeros((), dtype=vecs.dtype, device=vecs.device), vecs)
+
+
+def _is_zero_from_stats(stats: List[int], thresholded: bool, masked: bool) -> List[bool]:
+    bit = (STAT_NONZERO_TM if thresholded else STAT_NONZERO_M) if masked else \
+        (STAT_NONZERO_T if thresholded else STAT_NONZERO)
+    return [not (f & bit) for f in stats]
+
+
+def is_zero_flow(flow: Union[np.ndarray, torch.Tensor], thresholded: bool = None) -> torch.Tensor:
+    """reference utils.py:919-938: (N,) bool, True where the (thresholded) flow is zero everywhere."""
+    flow, stats = _valid_vecs(flow, error_string="Error checking whether flow is zero: ", want_stats=True)
+    thresholded = True if thresholded is None else thresholded
+    if not isinstance(thresholded, bool):
+        raise TypeError("Error checking whether flow is zero: Thresholded needs to be a boolean")
+    _ops.require_cuda(flow, "flow")
+    return torch.tensor(_is_zero_from_stats(stats, thresholded, False), dtype=torch.bool, device=flow.device)
+
+
+# ----------------------------------------------------------------------------------------------------
+# the hot path
+# ----------------------------------------------------------------------------------------------------
+
+def get_flow_endpoints(flow: torch.Tensor, ref: str) -> tuple:
+    """reference utils.py:1045-1058.  Differentiable w.r.t. the flow.  (Inside apply_flow / apply_s_flow the
+    same two adds happen in registers; this function exists for callers that want the grids.)"""
+    s = 1.0 if ref == 's' else -1.0
+    h, w = flow.shape[-2:]
+    x = s * flow[:, 0] + torch.arange(w, device=flow.device, dtype=torch.float32)[None, None, :]
+    y = s * flow[:, 1] + torch.arange(h, device=flow.device, dtype=torch.float32)[None, :, None]
+    return x, y
+
+
+def grid_from_unstructured_data(x: torch.Tensor, y: torch.Tensor, data: torch.Tensor,
+                                mask: torch.Tensor = None) -> tuple:
+    """Inverse-bilinear splat of `data` located at (x, y) onto the regular grid (reference utils.py:1061-1154).
+    Returns (grid_data (N,C,H,W), density (N,H,W)); both differentiable w.r.t. x, y and data."""
+    _ops.require_cuda(data, "data")
+    return _ops.splat_xy(x, y, data, mask)
+
+
+def apply_s_flow(flow: torch.Tensor, data: torch.Tensor, mask: torch.Tensor = None,
+                 occlude_zero_flow: bool = None) -> tuple:
+    """Forward warp by an 's' flow (reference utils.py:1157-1205).  Returns (warped (N,C,H,W), mask (N,H,W))."""
+    occlude_zero_flow = True if occlude_zero_flow is None else occlude_zero_flow
+    _ops.require_cuda(flow, "flow")
+    out, _density, wmask, _valid = _ops.splat_flow(flow, data.float(), None, mask, 1.0, bool(occlude_zero_flow),
+                                                   VALID_NONE)
+    return out, wmask
+
+
+def _restore_shape(result: torch.Tensor, target_dims: int) -> torch.Tensor:
+    """reference utils.py:603-610"""
+    if result.shape[0] == 1:
+        if target_dims == 2:
+            return result[0, 0]
+        if target_dims == 3:
+            return result[0]
+    elif target_dims == 2:
+        return result[:, 0]
+    return result
+
+
+def _restore_dtype(result: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """reference utils.py:614-618"""
+    if not dtype.is_floating_point:
+        result = torch.round(result)
+        if dtype == torch.uint8:
+            result = torch.clamp(result, 0, 255)
+    return result.to(dtype)
+
+
+def apply_flow(flow: Union[np.ndarray, torch.Tensor], target: torch.Tensor, ref: str,
+               mask: Union[np.ndarray, torch.Tensor] = None) -> torch.Tensor:
+    """Warps `target` with `flow` (reference utils.py:469-620).  Differentiable w.r.t. flow and target.
+
+    :param flow: (2,H,W), (H,W,2), (N,2,H,W) or (N,H,W,2)
+    :param target: (H,W), (C,H,W) or (N,C,H,W); batch sizes 1 and N broadcast
+    :param ref: 't' or 's'
+    :param mask: (H,W) or (N,H,W) flow mask, only relevant for 's' flows
+    """
+    ref = get_valid_ref(ref)
+    flow, stats = _valid_vecs(flow, error_string="Error applying flow to a target: ", want_stats=True)
+    if stats is not None and all(_is_zero_from_stats(stats, True, False)):       # utils.py:497-498
+        return target
+    if not isinstance(target, torch.Tensor):
+        raise TypeError("Error applying flow to a target: Target needs to be a torch tensor")
+    if len(target.shape) not in [2, 3, 4]:
+        raise ValueError("Error applying flow to a target: Target tensor needs to have shape H-W, C-H-W, or N-C-H-W")
+    if target.shape[-2:] != flow.shape[-2:]:
+        raise ValueError("Error applying flow to a target: Target height and width needs to match flow field array")
+    if mask is not None:
+        mask = get_valid_mask(mask, desired_shape=(flow.shape[0],) + tuple(flow.shape[2:]))
+    _ops.require_cuda(flow, "flow")
+
+    target_dtype = target.dtype
+    t = target.to(torch.float)
+    if t.device != flow.device:
+        t = t.to(flow.device)
+    if mask is not None and mask.device != flow.device:
+        mask = mask.to(flow.device)
+    target_dims = t.dim()
+    if target_dims == 2:
+        t = t[None, None]
+    elif target_dims == 3:
+        t = t[None]
+    if t.shape[0] != flow.shape[0] and t.shape[0] != 1 and flow.shape[0] != 1:
+        raise ValueError("Error applying flow to target: Batch dimensions for flow ({}) and target ({}) don't match"
+                         .format(flow.shape[0], t.shape[0]))
+
+    if ref == 't':
+        result, _ = _ops.warp_t(flow, t)                                          # utils.py:541-555
+    else:
+        result, _d, _w, _v = _ops.splat_flow(flow, t, None, mask, 1.0, True, VALID_NONE)   # utils.py:576
+    return _restore_dtype(_restore_shape(result, target_dims), target_dtype)

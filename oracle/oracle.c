@@ -103,57 +103,76 @@ void orc_warp_t_fwd(const float *flow, float sign, const float *tgt, float *out,
  * output pixels, corners nw,ne,sw,se (ATen grid_sampler_2d_backward, one
  * batch item per thread).  gflow replays the chain  grid_sample' -> x(W-1)/2
  * -> normalise_coords' (/(W-1), x2) -> minus. */
+typedef struct { float nw, ne, sw, se, ex, wx, sy, ny; int64_t o_nw, o_ne, o_sw, o_se; int b_nw, b_ne, b_sw, b_se; } orc_taps;
+
+static inline orc_taps orc_make_taps(const float *flow, float sign, int n, int i, int j, int H, int W)
+{
+    const int64_t HW = (int64_t)H * W, p = (int64_t)i * W + j;
+    orc_taps t;
+    float cx = (float)j - sign * flow[((int64_t)n * 2 + 0) * HW + p];
+    float cy = (float)i - sign * flow[((int64_t)n * 2 + 1) * HW + p];
+    float ix = orc_round_trip(cx, (float)(W - 1));
+    float iy = orc_round_trip(cy, (float)(H - 1));
+    float x0 = floorf(ix), y0 = floorf(iy);
+    float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+    t.ex = x1 - ix; t.wx = ix - x0; t.sy = y1 - iy; t.ny = iy - y0;
+    t.nw = t.ex * t.sy; t.ne = t.wx * t.sy; t.sw = t.ex * t.ny; t.se = t.wx * t.ny;
+    t.b_nw = orc_inb(x0, y0, H, W); t.b_ne = orc_inb(x1, y0, H, W);
+    t.b_sw = orc_inb(x0, y1, H, W); t.b_se = orc_inb(x1, y1, H, W);
+    t.o_nw = t.b_nw ? (int64_t)y0 * W + (int64_t)x0 : 0;
+    t.o_ne = t.b_ne ? (int64_t)y0 * W + (int64_t)x1 : 0;
+    t.o_sw = t.b_sw ? (int64_t)y1 * W + (int64_t)x0 : 0;
+    t.o_se = t.b_se ? (int64_t)y1 * W + (int64_t)x1 : 0;
+    return t;
+}
+
 void orc_warp_t_bwd(const float *flow, float sign, const float *tgt, const float *gout,
                     float *gflow, float *gtgt, int N, int C, int H, int W)
 {
     const int64_t HW = (int64_t)H * W;
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-    if (gtgt) memset(gtgt, 0, sizeof(float) * (size_t)N * C * HW);
-#pragma omp parallel for schedule(static)
-    for (int n = 0; n < N; ++n) {
-        for (int i = 0; i < H; ++i) {
-            for (int j = 0; j < W; ++j) {
-                int64_t p = (int64_t)i * W + j;
-                float cx = (float)j - sign * flow[((int64_t)n * 2 + 0) * HW + p];
-                float cy = (float)i - sign * flow[((int64_t)n * 2 + 1) * HW + p];
-                float ix = orc_round_trip(cx, wm1);
-                float iy = orc_round_trip(cy, hm1);
-                float x0 = floorf(ix), y0 = floorf(iy);
-                float x1 = x0 + 1.0f, y1 = y0 + 1.0f;
-                float ex = x1 - ix, wx = ix - x0, sy = y1 - iy, ny = iy - y0;
-                float nw = ex * sy, ne = wx * sy, sw = ex * ny, se = wx * ny;
-                int b_nw = orc_inb(x0, y0, H, W), b_ne = orc_inb(x1, y0, H, W);
-                int b_sw = orc_inb(x0, y1, H, W), b_se = orc_inb(x1, y1, H, W);
-                int64_t o_nw = b_nw ? (int64_t)y0 * W + (int64_t)x0 : 0;
-                int64_t o_ne = b_ne ? (int64_t)y0 * W + (int64_t)x1 : 0;
-                int64_t o_sw = b_sw ? (int64_t)y1 * W + (int64_t)x0 : 0;
-                int64_t o_se = b_se ? (int64_t)y1 * W + (int64_t)x1 : 0;
-                float gix = 0.0f, giy = 0.0f;
-                for (int c = 0; c < C; ++c) {
-                    int64_t pl = ((int64_t)n * C + c) * HW;
-                    float g = gout[pl + p];
-                    if (gtgt) {
-                        if (b_nw) gtgt[pl + o_nw] += nw * g;
-                        if (b_ne) gtgt[pl + o_ne] += ne * g;
-                        if (b_sw) gtgt[pl + o_sw] += sw * g;
-                        if (b_se) gtgt[pl + o_se] += se * g;
+    if (gflow) {
+        /* a gather: any order */
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int n = 0; n < N; ++n)
+            for (int i = 0; i < H; ++i)
+                for (int j = 0; j < W; ++j) {
+                    int64_t p = (int64_t)i * W + j;
+                    orc_taps t = orc_make_taps(flow, sign, n, i, j, H, W);
+                    float gix = 0.0f, giy = 0.0f;
+                    for (int c = 0; c < C; ++c) {
+                        const float *s = tgt + ((int64_t)n * C + c) * HW;
+                        float g = gout[((int64_t)n * C + c) * HW + p];
+                        float a = t.b_nw ? s[t.o_nw] : 0.0f, b = t.b_ne ? s[t.o_ne] : 0.0f;
+                        float cc = t.b_sw ? s[t.o_sw] : 0.0f, d = t.b_se ? s[t.o_se] : 0.0f;
+                        gix += g * (-a * t.sy + b * t.sy - cc * t.ny + d * t.ny);
+                        giy += g * (-a * t.ex - b * t.wx + cc * t.ex + d * t.wx);
                     }
-                    if (gflow) {
-                        const float *t = tgt + pl;
-                        float a = b_nw ? t[o_nw] : 0.0f, b = b_ne ? t[o_ne] : 0.0f;
-                        float cc = b_sw ? t[o_sw] : 0.0f, d = b_se ? t[o_se] : 0.0f;
-                        gix += g * (-a * sy + b * sy - cc * ny + d * ny);
-                        giy += g * (-a * ex - b * wx + cc * ex + d * wx);
-                    }
-                }
-                if (gflow) {
                     float ggx = ((gix * (wm1 / 2.0f)) / wm1) * 2.0f;
                     float ggy = ((giy * (hm1 / 2.0f)) / hm1) * 2.0f;
                     gflow[((int64_t)n * 2 + 0) * HW + p] = -sign * ggx;
                     gflow[((int64_t)n * 2 + 1) * HW + p] = -sign * ggy;
                 }
+    }
+    if (gtgt) {
+        /* a scatter: every (n, c) plane accumulates in raster order of the output pixels, taps nw,ne,sw,se;
+         * planes are independent, so they run in parallel without changing any sum */
+#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+        for (int n = 0; n < N; ++n)
+            for (int c = 0; c < C; ++c) {
+                float *gs = gtgt + ((int64_t)n * C + c) * HW;
+                const float *go = gout + ((int64_t)n * C + c) * HW;
+                memset(gs, 0, sizeof(float) * (size_t)HW);
+                for (int i = 0; i < H; ++i)
+                    for (int j = 0; j < W; ++j) {
+                        orc_taps t = orc_make_taps(flow, sign, n, i, j, H, W);
+                        float g = go[(int64_t)i * W + j];
+                        if (t.b_nw) gs[t.o_nw] += t.nw * g;
+                        if (t.b_ne) gs[t.o_ne] += t.ne * g;
+                        if (t.b_sw) gs[t.o_sw] += t.sw * g;
+                        if (t.b_se) gs[t.o_se] += t.se * g;
+                    }
             }
-        }
     }
 }
 
