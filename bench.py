@@ -69,9 +69,9 @@ def smooth_flow(n, h, w, sigma, seed, device):
     return torch.nn.functional.interpolate(lo, size=(h, w), mode='bicubic', align_corners=True).contiguous()
 
 
-def make_inputs(n, device, seed0=2):
+def make_inputs(n, device, seed0=2, sigma=8.0):
     """SURVEY.md 8(d) cfg 2: smooth-random flow sigma = 8 px, uniform image, holed masks; synthetic."""
-    flow = smooth_flow(n, H, W, 8.0, seed0, device)
+    flow = smooth_flow(n, H, W, sigma, seed0, device)
     g = torch.Generator(device=device).manual_seed(seed0 + 1)
     img = torch.rand(n, C, H, W, generator=g, device=device)
     gout = torch.rand(n, C, H, W, generator=g, device=device)
@@ -173,6 +173,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=4, help='batch of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--sigma', type=float, default=8.0, help='flow magnitude (px) of the synthetic field; 8 = the named config')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
 
@@ -218,7 +219,7 @@ def main():
 
     n = args.batch
     px = n * H * W
-    flow, img, mask, tmask, gout = make_inputs(n, dev, seed0=2 + 10 * rank)
+    flow, img, mask, tmask, gout = make_inputs(n, dev, seed0=2 + 10 * rank, sigma=args.sigma)
 
     # ---------------------------------------------------------------- device-resident timing
     for _ in range(args.warmup):

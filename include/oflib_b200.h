@@ -53,6 +53,12 @@ const char *ofb_error_string(int status);
 int64_t ofb_launch_count(void);
 void ofb_launch_count_reset(void);
 
+/* Self-test: counts the float bit patterns b in [lo_bits, hi_bits) (both signs) for which the kernels' coordinate
+ * round trip (constant-reciprocal division, d = W-1 or H-1) differs from the one evaluated with IEEE division as
+ * the reference does (utils.py:462-465 + ATen GridSampler.h:31).  *mismatches (device, zeroed by the caller) must
+ * stay 0: the validity masks depend on it. */
+int ofb_selftest_div(float d, uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches, void *stream);
+
 /* One pass over a flow field: replaces get_valid_vecs' isfinite().all() (utils.py:98), is_zero_flow
  * (utils.py:919-938) and Flow.is_zero (flow_class.py:1226-1244).  flags[N] must be zero on entry and
  * receives the OR of the OFB_STAT_* bits per batch item.  mask (N,H,W) may be NULL (then the *_M

@@ -28,6 +28,37 @@ __device__ __forceinline__ float round_trip(float c, float size_m1)
     return __fmul_rn(g, size_m1);
 }
 
+// x / d for a loop-invariant divisor d with rcp = RN(1/d) computed once (host, IEEE division).
+// q0 = RN(x*rcp) is within 2 ulp of x/d; each step  q += RN(x - d*q) * rcp  (the residual is exact with an FMA)
+// brings a value within 1 ulp to the correctly rounded quotient (Markstein's theorem), so two steps from q0 give
+// RN(x/d) for |x| < 2^24 as long as the quotient is a normal number.  Denormal quotients can differ from IEEE in
+// exact-halfway cases, which is immaterial here: the round trip subtracts 1 next, absorbing anything below 2^-25.
+// |x| >= 2^24 takes the IEEE division.  tests/test_gpu_parity.py::test_round_trip_exhaustive checks
+// round_trip_fast == round_trip over EVERY float bit pattern for the image sizes in use.
+struct ExactDiv {
+    float d, rcp;
+};
+
+__device__ __forceinline__ float div_exact(float x, const ExactDiv &e)
+{
+    if (!(fabsf(x) < 16777216.0f)) return __fdiv_rn(x, e.d);
+    float q = __fmul_rn(x, e.rcp);
+    q = __fmaf_rn(__fmaf_rn(-e.d, q, x), e.rcp, q);
+    q = __fmaf_rn(__fmaf_rn(-e.d, q, x), e.rcp, q);
+    return q;
+}
+
+// pixel -> normalised -> pixel with the division done by div_exact (bit-identical to round_trip)
+__device__ __forceinline__ float round_trip_fast(float c, const ExactDiv &e)
+{
+    float g = __fmul_rn(c, 2.0f);
+    g = div_exact(g, e);
+    g = __fsub_rn(g, 1.0f);
+    g = __fadd_rn(g, 1.0f);
+    g = __fmul_rn(g, 0.5f);
+    return __fmul_rn(g, e.d);
+}
+
 // The four bilinear taps of one sample position (zero padding: out-of-bounds taps read as 0).
 struct Taps {
     float nw, ne, sw, se;       // weights

@@ -42,9 +42,36 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict
     if ((threadIdx.x & 31) == 0 && acc != 0) atomicOr(flags + n, acc);
 }
 
+// self-test: the coordinate round trip with the constant-reciprocal division must equal the one with the IEEE
+// division for every float bit pattern (both signs)
+__global__ void div_selftest_kernel(float d, float rcp, uint32_t lo, uint32_t hi, unsigned long long *bad)
+{
+    const ExactDiv e{d, rcp};
+    unsigned long long local = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < hi; b += stride) {
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            const float x = __uint_as_float((uint32_t)b | (sgn ? 0x80000000u : 0u));
+            const float q = round_trip_fast(x, e), r = round_trip(x, d);
+            if (__float_as_uint(q) != __float_as_uint(r) && !(q != q && r != r)) ++local;
+        }
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 }  // namespace ofb
 
 using namespace ofb;
+
+extern "C" int ofb_selftest_div(float d, uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches,
+                                void *stream)
+{
+    if (!mismatches || !(d >= 1.0f)) return OFB_EINVAL;
+    div_selftest_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(d, 1.0f / d, lo_bits, hi_bits,
+                                                                                 mismatches);
+    OFB_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int ofb_flow_stats(const float *flow, const uint8_t *mask, int32_t *flags,
                               int N, int H, int W, void *stream)

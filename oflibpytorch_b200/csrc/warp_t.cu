@@ -1,11 +1,22 @@
 // W: backward warp ('t' flows) with fused validity, and its adjoint.
 //
-// Replaces reference utils.py:541-555 (apply_flow ref 't') and the mask tracking of Flow.apply
-// (flow_class.py:896-898,922-934).  One thread owns VEC horizontally adjacent output pixels: the two
-// flow planes are read with one 128-bit load each, every payload channel is written with one 128-bit
-// store, and the 4*VEC bilinear taps per channel go through the read-only path (neighbouring threads
-// hit the same 128 B lines, so the source is fetched from HBM once).
+// Replaces reference utils.py:541-555 (apply_flow ref 't': grid - flow, normalise_coords, grid_sample(bilinear,
+// zeros, align_corners=True)) and the mask tracking of Flow.apply (flow_class.py:896-898,922-934).
+//
+// Forward, staged variant (the fast path).  A CTA owns a 64x32 tile of OUTPUT pixels, lanes along x, 8 rows per
+// thread.  Phase 1 streams the tile's flow (coalesced, 16 loads in flight per thread) and reduces the bounding box
+// of all sample positions; phase 2 has one thread issue TMA box copies (cp.async.bulk.tensor.3d) of that source
+// region -- all payload channels and the byte mask -- into shared memory, the TMA unit zero-filling whatever lies
+// outside the image (= padding_mode='zeros'); phase 3 evaluates the 4 taps per channel as LDS [reg + imm] off ONE
+// address register per pixel: no bounds predicates, no 64-bit address arithmetic, one wavefront per tap load.
+// Tiles whose footprint exceeds the box (violent flows) take the direct path below, per tile.
+//
+// Direct variant: one thread per output pixel, taps through the read-only path with explicit bounds predicates.
+#include <climits>
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ofb {
 
@@ -19,104 +30,360 @@ struct WarpFwdParams {
     int N, C, H, W;
 };
 
-template <int VEC> struct FVec;
-template <> struct FVec<1> { float v[1]; };
-template <> struct FVec<4> { float v[4]; };
+// ------------------------------------------------------------------------------------------------
+// direct forward: taps through the read-only path
+// ------------------------------------------------------------------------------------------------
+struct CoordCtx {     // loop-invariant pieces of the coordinate round trip
+    ExactDiv dw, dh;  // (W-1, 1/(W-1)), (H-1, 1/(H-1))
+    float sign;
+};
 
-template <int VEC>
-__device__ __forceinline__ void load_vec(const float *__restrict__ p, float (&v)[VEC])
+// sample position of output pixel (xf, yf) in fp32, exactly as the reference computes it:
+// fma(-sign, f, x) == x - sign*f with a single rounding because sign*f is exact (utils.py:548-550)
+__device__ __forceinline__ void sample_pos(const CoordCtx &cc, float fx, float fy, float xf, float yf, float &ix, float &iy)
 {
-    if constexpr (VEC == 4) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-        v[0] = __ldg(p);
-    }
+    ix = round_trip_fast(__fmaf_rn(-cc.sign, fx, xf), cc.dw);
+    iy = round_trip_fast(__fmaf_rn(-cc.sign, fy, yf), cc.dh);
 }
 
-template <int VEC>
-__device__ __forceinline__ void store_vec(float *__restrict__ p, const float (&v)[VEC])
+struct PixGeom {                 // tap geometry of one output pixel
+    float wnw, wne, wsw, wse;    // bilinear weights
+    int o;                       // yi*W + xi of the NW tap (only dereferenced under the predicates below)
+    bool pnw, pne, psw, pse;     // tap inside the image (zero padding otherwise)
+};
+
+__device__ __forceinline__ PixGeom pix_geom(float ix, float iy, int W, float wm1, float hm1)
 {
-    if constexpr (VEC == 4) {
-        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-        p[0] = v[0];
-    }
+    PixGeom g;
+    const float x0 = floorf(ix), y0 = floorf(iy);
+    const float ex = __fsub_rn(__fadd_rn(x0, 1.0f), ix), wx = __fsub_rn(ix, x0);
+    const float sy = __fsub_rn(__fadd_rn(y0, 1.0f), iy), ny = __fsub_rn(iy, y0);
+    g.wnw = __fmul_rn(ex, sy); g.wne = __fmul_rn(wx, sy);
+    g.wsw = __fmul_rn(ex, ny); g.wse = __fmul_rn(wx, ny);
+    // x1 = x0 + 1 in [0, W-1]  <=>  x0 in [-1, W-2]  (exact for |x0| < 2^24; beyond that everything is false)
+    const bool bx0 = (x0 >= 0.0f) && (x0 <= wm1), bx1 = (x0 >= -1.0f) && (x0 <= wm1 - 1.0f);
+    const bool by0 = (y0 >= 0.0f) && (y0 <= hm1), by1 = (y0 >= -1.0f) && (y0 <= hm1 - 1.0f);
+    g.pnw = bx0 && by0; g.pne = bx1 && by0; g.psw = bx0 && by1; g.pse = bx1 && by1;
+    // clamp before converting: outside [-1, size-1] every predicate is false and the offset is never used
+    const int xi = (int)fminf(fmaxf(x0, -1.0f), wm1), yi = (int)fminf(fmaxf(y0, -1.0f), hm1);
+    g.o = yi * W + xi;
+    return g;
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256) warp_t_fwd_kernel(const WarpFwdParams p)
+// The four taps of one plane.  `north` points at the NW tap, `south` one image row below; each is ONE 64-bit
+// address, the east taps are immediate offsets.  Out-of-image taps are not loaded and read as zero.
+template <typename T>
+__device__ __forceinline__ void load_taps(const T *__restrict__ north, const T *__restrict__ south, const PixGeom &g,
+                                          T &a, T &b, T &c, T &d)
 {
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int n = blockIdx.z;
-    if (x >= p.W || y >= p.H) return;
+    a = b = c = d = T(0);
+    if (g.pnw) a = __ldg(north);
+    if (g.pne) b = __ldg(north + 1);
+    if (g.psw) c = __ldg(south);
+    if (g.pse) d = __ldg(south + 1);
+}
+
+__device__ __forceinline__ float blend4(const PixGeom &g, float a, float b, float c, float d)
+{
+    float r = __fmul_rn(a, g.wnw);      // ATen's CPU accumulation order (oracle/oracle.c)
+    r = __fmaf_rn(b, g.wne, r);
+    r = __fmaf_rn(c, g.wsw, r);
+    return __fmaf_rn(d, g.wse, r);
+}
+
+// Per-thread base pointers of one batch item (computed once; everything below is 32-bit offsets from them).
+struct ItemPtrs {
+    const float *src;         // payload planes of this item, channel group already applied
+    float *out;               // output planes of this item, channel group already applied
+    const uint8_t *smask;     // payload mask of this item or nullptr
+    const uint8_t *fmask;     // flow mask of this item or nullptr
+    uint8_t *valid;           // validity plane of this item
+};
+
+// One output pixel through global memory: channels [0, CN) (CN = 0: cn_rt channels, runtime loop).
+// pix = y*W + x of the output pixel; c_first = absolute index of channel 0 (for add_flow).
+template <int CN, bool WANT_VALID>
+__device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const ItemPtrs &ip, const PixGeom &g,
+                                                  int pix, float fx, float fy, int c_first, int cn_rt)
+{
     const int HW = p.H * p.W;
-    const int pix = y * p.W + x;
-    const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
-
-    float fx[VEC], fy[VEC];
-    const float *fl = p.flow + (int64_t)n * p.flow_bs;
-    load_vec<VEC>(fl + pix, fx);
-    load_vec<VEC>(fl + HW + pix, fy);
-
-    Taps t[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        const float cx = __fsub_rn((float)(x + k), __fmul_rn(p.sign, fx[k]));   // utils.py:548-550
-        const float cy = __fsub_rn((float)y, __fmul_rn(p.sign, fy[k]));
-        t[k] = make_taps(round_trip(cx, wm1), round_trip(cy, hm1), p.H, p.W);
-    }
-
-    if (p.valid) {
-        const uint8_t *sm = p.src_mask ? p.src_mask + (int64_t)n * p.src_mask_bs : nullptr;
-        const uint8_t *fm = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs + pix : nullptr;
-        uint8_t v[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            float a, b, c, d;
-            if (sm) {
-                a = t[k].o_nw >= 0 ? (float)__ldg(sm + t[k].o_nw) : 0.0f;
-                b = t[k].o_ne >= 0 ? (float)__ldg(sm + t[k].o_ne) : 0.0f;
-                c = t[k].o_sw >= 0 ? (float)__ldg(sm + t[k].o_sw) : 0.0f;
-                d = t[k].o_se >= 0 ? (float)__ldg(sm + t[k].o_se) : 0.0f;
-            } else {
-                a = t[k].o_nw >= 0 ? 1.0f : 0.0f;
-                b = t[k].o_ne >= 0 ? 1.0f : 0.0f;
-                c = t[k].o_sw >= 0 ? 1.0f : 0.0f;
-                d = t[k].o_se >= 0 ? 1.0f : 0.0f;
-            }
-            const float mch = blend(t[k], a, b, c, d);                     // flow_class.py:898
-            bool ok = mch > p.thresh;                                       // flow_class.py:922
-            if (fm) ok = ok && (fm[k] != 0);                                // flow_class.py:934
-            v[k] = ok ? 1 : 0;
-        }
-        uint8_t *vp = p.valid + (int64_t)n * HW + pix;
-        if constexpr (VEC == 4) {
-            *reinterpret_cast<uchar4 *>(vp) = make_uchar4(v[0], v[1], v[2], v[3]);
+    if (WANT_VALID) {
+        float a, b, c, d;
+        if (ip.smask) {
+            uint8_t ua, ub, uc, ud;
+            load_taps<uint8_t>(ip.smask + g.o, ip.smask + (g.o + p.W), g, ua, ub, uc, ud);
+            a = ua ? 1.0f : 0.0f; b = ub ? 1.0f : 0.0f; c = uc ? 1.0f : 0.0f; d = ud ? 1.0f : 0.0f;
         } else {
-            vp[0] = v[0];
+            a = g.pnw ? 1.0f : 0.0f; b = g.pne ? 1.0f : 0.0f; c = g.psw ? 1.0f : 0.0f; d = g.pse ? 1.0f : 0.0f;
+        }
+        bool ok = blend4(g, a, b, c, d) > p.thresh;                                  // flow_class.py:898,922
+        if (ip.fmask) ok = ok && (__ldg(ip.fmask + pix) != 0);                       // flow_class.py:934
+        ip.valid[pix] = ok ? 1 : 0;
+    }
+    if (CN > 0) {
+#pragma unroll
+        for (int c = 0; c < CN; ++c) {
+            const int e = c * HW + g.o;                                              // one int add per plane
+            float a, b, cc, d;
+            load_taps<float>(ip.src + e, ip.src + (e + p.W), g, a, b, cc, d);
+            float r = blend4(g, a, b, cc, d);
+            if (p.add_flow != 0.0f && c_first + c < 2)                               // flow_class.py:1804,1808
+                r = __fadd_rn(__fmul_rn(p.add_flow, (c_first + c) == 0 ? fx : fy), r);
+            ip.out[c * HW + pix] = r;
+        }
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < cn_rt; ++c) {
+            const int64_t e = (int64_t)c * HW + g.o;
+            float a, b, cc, d;
+            load_taps<float>(ip.src + e, ip.src + (e + p.W), g, a, b, cc, d);
+            float r = blend4(g, a, b, cc, d);
+            if (p.add_flow != 0.0f && c_first + c < 2)
+                r = __fadd_rn(__fmul_rn(p.add_flow, (c_first + c) == 0 ? fx : fy), r);
+            ip.out[(int64_t)c * HW + pix] = r;
         }
     }
+}
 
-    const float *src = p.src + (int64_t)n * p.src_bs;
-    float *out = p.out + (int64_t)n * p.C * HW + pix;
+__device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, int n, int c_off)
+{
+    const int64_t HW = (int64_t)p.H * p.W;
+    ItemPtrs ip;
+    ip.src = p.src + (int64_t)n * p.src_bs + c_off * HW;
+    ip.out = p.out + ((int64_t)n * p.C + c_off) * HW;
+    ip.smask = p.src_mask ? p.src_mask + (int64_t)n * p.src_mask_bs : nullptr;
+    ip.fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
+    ip.valid = p.valid + (int64_t)n * HW;
+    // Opaque to the optimiser from here on: otherwise ptxas re-derives base + n*stride in 64-bit arithmetic at every
+    // use (5 instructions per tap pair, measured) instead of keeping five pointers in registers.
+    asm volatile("" : "+l"(ip.src), "+l"(ip.out), "+l"(ip.smask), "+l"(ip.fmask), "+l"(ip.valid));
+    return ip;
+}
+
+constexpr int kDirRows = 4;    // rows per thread; CTA tile = 64 x 16 (2 warps across x, 4 across y)
+
+template <int CN, bool WANT_VALID>
+__global__ void __launch_bounds__(256) warp_t_fwd_direct_kernel(const WarpFwdParams p, const CoordCtx cc)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * (4 * kDirRows) + (warp >> 1) * kDirRows;
+    const int n = blockIdx.z;
+    if (x >= p.W) return;
+    const int HW = p.H * p.W;
+    const float *fl = p.flow + (int64_t)n * p.flow_bs;
+    float fx[kDirRows], fy[kDirRows];
+#pragma unroll
+    for (int r = 0; r < kDirRows; ++r) {
+        const int q = min(y0 + r, p.H - 1) * p.W + x;
+        fx[r] = __ldg(fl + q);
+        fy[r] = __ldg(fl + (HW + q));
+    }
+    const float xf = (float)x, wm1 = cc.dw.d, hm1 = cc.dh.d;
+    const ItemPtrs ip = item_ptrs(p, n, 0);
+    const int rows = min(kDirRows, p.H - y0);
+#pragma unroll
+    for (int r = 0; r < kDirRows; ++r) {
+        if (r >= rows) break;
+        float ix, iy;
+        sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r), ix, iy);
+        const PixGeom g = pix_geom(ix, iy, p.W, wm1, hm1);
+        warp_pixel_direct<CN, WANT_VALID>(p, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// staged forward
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileW = 64, kTileH = 32, kRows = 8;        // 8 warps: 2 across x, 4 across y, 8 rows per thread
+constexpr int kBoxW = 80, kBoxH = 48;                     // staged source region (floats): tile + 16 of slack
+constexpr int kPlane = kBoxW * kBoxH;                     // elements per staged channel
+constexpr int kMBoxW = 96;                                // byte-mask box is wider: its origin is 16-pixel aligned
+constexpr int kMaxCN = 4;                                 // payload channels staged per launch
+// TMA needs the box origin 16-byte aligned along x: multiples of 4 floats / 16 mask bytes (measured: anything else
+// raises an illegal-instruction fault).  Rounding the origin down costs at most 3 (15) columns of the box.
+
+struct StageCtl {
+    unsigned long long bar;   // mbarrier
+    int minx, maxx, miny, maxy;
+    int mode;                 // 0 staged, 1 direct (footprint too large), 2 nothing in bounds
+};
+
+constexpr int staged_smem_bytes(int cn, int vmode)
+{
+    return kPlane * 4 * cn + (vmode == 2 ? kMBoxW * kBoxH : 0) + 64;
+}
+
+// CN    payload channels handled by this launch (1..4), planes [c_off, c_off + CN) of C_total
+// VMODE 0: no validity output; 1: validity with an all-true payload mask; 2: validity with a staged payload mask
+template <int CN, int VMODE>
+__global__ void __launch_bounds__(256, 3) warp_t_fwd_staged_kernel(const WarpFwdParams p,
+                                                                   const __grid_constant__ CUtensorMap src_map,
+                                                                   const __grid_constant__ CUtensorMap mask_map,
+                                                                   const int c_off, const CoordCtx cc)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float *tile = reinterpret_cast<float *>(smem);
+    uint8_t *mtile = smem + kPlane * 4 * CN;
+    StageCtl &ctl = *reinterpret_cast<StageCtl *>(smem + kPlane * 4 * CN + (VMODE == 2 ? kMBoxW * kBoxH : 0));
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * kTileW + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * kTileH + (warp >> 1) * kRows;
+    const int n = blockIdx.z;
+    const int HW = p.H * p.W;
+    const int xc = min(x, p.W - 1);                       // clamped copies for loads; stores are predicated
+    const float xf = (float)x;
+
+    if (threadIdx.x == 0) {
+        ctl.minx = INT_MAX; ctl.miny = INT_MAX; ctl.maxx = INT_MIN; ctl.maxy = INT_MIN;
+        mbar_init(reinterpret_cast<uint64_t *>(&ctl.bar), 1);
+    }
+    __syncthreads();
+
+    // ---- phase 1: flow -> sample positions, footprint of the tile
+    float ix[kRows], iy[kRows];
+    {
+        const float *fl = p.flow + (int64_t)n * p.flow_bs + xc;
+        float fx[kRows], fy[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int yc = min(y0 + r, p.H - 1);
+            fx[r] = __ldg(fl + yc * p.W);
+            fy[r] = __ldg(fl + HW + yc * p.W);
+        }
+        const float wm1 = cc.dw.d, hm1 = cc.dh.d;
+        int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r), ix[r], iy[r]);
+            const float fx0 = floorf(ix[r]), fy0 = floorf(iy[r]);
+            // pixels with at least one tap inside the image: x0 in [-1, W-1], y0 in [-1, H-1]
+            const bool any = (x < p.W) && (y0 + r < p.H) && fx0 >= -1.0f && fx0 <= wm1 && fy0 >= -1.0f && fy0 <= hm1;
+            const int xi = any ? (int)fx0 : INT_MAX, yi = any ? (int)fy0 : INT_MAX;
+            minx = min(minx, xi); miny = min(miny, yi);
+            maxx = max(maxx, any ? xi : INT_MIN); maxy = max(maxy, any ? yi : INT_MIN);
+        }
+        minx = __reduce_min_sync(0xffffffffu, minx); maxx = __reduce_max_sync(0xffffffffu, maxx);
+        miny = __reduce_min_sync(0xffffffffu, miny); maxy = __reduce_max_sync(0xffffffffu, maxy);
+        if (lane == 0 && minx != INT_MAX) {
+            atomicMin(&ctl.minx, minx); atomicMax(&ctl.maxx, maxx);
+            atomicMin(&ctl.miny, miny); atomicMax(&ctl.maxy, maxy);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread decides and issues the box copies
+    if (threadIdx.x == 0) {
+        int mode = 0;
+        if (ctl.minx == INT_MAX) mode = 2;
+        else if (ctl.maxx + 2 - (ctl.minx & ~3) > kBoxW || ctl.maxy - ctl.miny + 2 > kBoxH) mode = 1;
+        ctl.mode = mode;
+        if (mode == 0) {
+            mbar_expect_tx(reinterpret_cast<uint64_t *>(&ctl.bar),
+                           (uint32_t)(kPlane * 4 * CN + (VMODE == 2 ? kMBoxW * kBoxH : 0)));
+            tma_load_3d(tile, &src_map, ctl.minx & ~3, ctl.miny, ((p.src_bs == 0) ? 0 : n * p.C) + c_off,
+                        reinterpret_cast<uint64_t *>(&ctl.bar));
+            if (VMODE == 2)
+                tma_load_3d(mtile, &mask_map, ctl.minx & ~15, ctl.miny, (p.src_mask_bs == 0) ? 0 : n,
+                            reinterpret_cast<uint64_t *>(&ctl.bar));
+        }
+    }
+    __syncthreads();
+    const int mode = ctl.mode;
+    const int ox = ctl.minx & ~3, oy = ctl.miny;      // origin of the payload box
+    const int mdx = ox - (ctl.minx & ~15);            // payload-box column -> mask-box column
+
+    if (mode == 1) {   // footprint larger than the box: this tile goes through global memory
+        if (x >= p.W) return;
+        const float *fl = p.flow + (int64_t)n * p.flow_bs + x;
+        ItemPtrs ip = item_ptrs(p, n, c_off);
+        if (VMODE != 2) ip.smask = nullptr;
 #pragma unroll 1
-    for (int c = 0; c < p.C; ++c) {
-        const float *s = src + (int64_t)c * HW;
-        float r[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            const float a = ldg_or_zero(s, t[k].o_nw), b = ldg_or_zero(s, t[k].o_ne);
-            const float cc = ldg_or_zero(s, t[k].o_sw), d = ldg_or_zero(s, t[k].o_se);
-            r[k] = blend(t[k], a, b, cc, d);
+        for (int r = 0; r < kRows; ++r) {            // positions are recomputed: keeps this cold path small
+            const int y = y0 + r;
+            if (y >= p.H) break;
+            const float fx = __ldg(fl + y * p.W), fy = __ldg(fl + HW + y * p.W);
+            float jx, jy;
+            sample_pos(cc, fx, fy, xf, (float)y, jx, jy);
+            const PixGeom g = pix_geom(jx, jy, p.W, cc.dw.d, cc.dh.d);
+            warp_pixel_direct<CN, VMODE != 0>(p, ip, g, y * p.W + x, fx, fy, c_off, CN);
         }
-        if (p.add_flow != 0.0f && c < 2) {                                  // flow_class.py:1804,1808
+        return;
+    }
+    if (mode == 0) mbar_wait(reinterpret_cast<uint64_t *>(&ctl.bar), 0);
+
+    // ---- phase 3: taps from shared memory, no bounds logic (the TMA unit zero-filled what lies outside)
+    float *out = p.out + ((int64_t)n * p.C + c_off) * HW + x;
+    const float wm1 = cc.dw.d, hm1 = cc.dh.d;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k)
-                r[k] = __fadd_rn(__fmul_rn(p.add_flow, c == 0 ? fx[k] : fy[k]), r[k]);
+    for (int r = 0; r < kRows; ++r) {
+        const float fx0 = floorf(ix[r]), fy0 = floorf(iy[r]);
+        const bool any = mode == 0 && fx0 >= -1.0f && fx0 <= wm1 && fy0 >= -1.0f && fy0 <= hm1;
+        const bool st = (x < p.W) && (y0 + r < p.H);
+        const int xi = any ? (int)fx0 - ox : 0, yi = any ? (int)fy0 - oy : 0;
+        const int off = yi * kBoxW + xi;
+        const float ex = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[r]), wx = __fsub_rn(ix[r], fx0);
+        const float sy = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[r]), ny = __fsub_rn(iy[r], fy0);
+        const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
+        const int pix = (y0 + r) * p.W;
+
+        if (VMODE != 0) {   // the payload mask rides through the same weights (flow_class.py:898,922,934)
+            float a, b, c, d;
+            if (VMODE == 2) {
+                const uint8_t *m = mtile + yi * kMBoxW + xi + mdx;
+                a = m[0] ? 1.0f : 0.0f; b = m[1] ? 1.0f : 0.0f;
+                c = m[kMBoxW] ? 1.0f : 0.0f; d = m[kMBoxW + 1] ? 1.0f : 0.0f;
+            } else {
+                const int gx = xi + ox, gy = yi + oy;
+                const bool bx0 = gx >= 0, bx1 = gx + 1 <= p.W - 1, by0 = gy >= 0, by1 = gy + 1 <= p.H - 1;
+                a = (bx0 && by0) ? 1.0f : 0.0f; b = (bx1 && by0) ? 1.0f : 0.0f;
+                c = (bx0 && by1) ? 1.0f : 0.0f; d = (bx1 && by1) ? 1.0f : 0.0f;
+            }
+            float m = __fmul_rn(a, wnw);
+            m = __fmaf_rn(b, wne, m);
+            m = __fmaf_rn(c, wsw, m);
+            m = __fmaf_rn(d, wse, m);
+            bool ok = any && (m > p.thresh);
+            if (st) {
+                if (p.flow_mask) ok = ok && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix + x) != 0);
+                p.valid[(int64_t)n * HW + pix + x] = ok ? 1 : 0;
+            }
         }
-        store_vec<VEC>(out + (int64_t)c * HW, r);
+        const float *t = tile + off;
+#pragma unroll
+        for (int c = 0; c < CN; ++c) {
+            float v = __fmul_rn(t[c * kPlane], wnw);
+            v = __fmaf_rn(t[c * kPlane + 1], wne, v);
+            v = __fmaf_rn(t[c * kPlane + kBoxW], wsw, v);
+            v = __fmaf_rn(t[c * kPlane + kBoxW + 1], wse, v);
+            v = any ? v : 0.0f;
+            if (p.add_flow != 0.0f && c_off + c < 2 && st) {                          // flow_class.py:1804,1808
+                const float f = __ldg(p.flow + (int64_t)n * p.flow_bs + (c_off + c) * HW + pix + x);
+                v = __fadd_rn(__fmul_rn(p.add_flow, f), v);
+            }
+            if (st) out[(int64_t)c * HW + pix] = v;
+        }
+    }
+}
+
+typedef void (*StagedKernel)(const WarpFwdParams, const CUtensorMap, const CUtensorMap, const int, const CoordCtx);
+
+template <int CN>
+static StagedKernel staged_kernel_for(int vmode)
+{
+    if (vmode == 0) return warp_t_fwd_staged_kernel<CN, 0>;
+    if (vmode == 1) return warp_t_fwd_staged_kernel<CN, 1>;
+    return warp_t_fwd_staged_kernel<CN, 2>;
+}
+
+static StagedKernel staged_kernel(int cn, int vmode)
+{
+    switch (cn) {
+        case 1: return staged_kernel_for<1>(vmode);
+        case 2: return staged_kernel_for<2>(vmode);
+        case 3: return staged_kernel_for<3>(vmode);
+        default: return staged_kernel_for<4>(vmode);
     }
 }
 
@@ -129,10 +396,9 @@ struct WarpBwdParams {
 };
 
 // v0 adjoint: gflow is a gather; gsrc is scattered with one red.global.add.f32 per tap.
-template <int VEC>
 __global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p)
 {
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int n = blockIdx.z;
     if (x >= p.W || y >= p.H) return;
@@ -140,65 +406,43 @@ __global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p)
     const int pix = y * p.W + x;
     const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
 
-    float fx[VEC], fy[VEC];
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
-    load_vec<VEC>(fl + pix, fx);
-    load_vec<VEC>(fl + HW + pix, fy);
-    Taps t[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        const float cx = __fsub_rn((float)(x + k), __fmul_rn(p.sign, fx[k]));
-        const float cy = __fsub_rn((float)y, __fmul_rn(p.sign, fy[k]));
-        t[k] = make_taps(round_trip(cx, wm1), round_trip(cy, hm1), p.H, p.W);
-    }
+    const float fx = __ldg(fl + pix), fy = __ldg(fl + HW + pix);
+    const float cx = __fsub_rn((float)x, __fmul_rn(p.sign, fx));
+    const float cy = __fsub_rn((float)y, __fmul_rn(p.sign, fy));
+    const Taps t = make_taps(round_trip(cx, wm1), round_trip(cy, hm1), p.H, p.W);
 
-    float gix[VEC], giy[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) gix[k] = giy[k] = 0.0f;
-
+    float gix = 0.0f, giy = 0.0f;
     const float *src = p.src ? p.src + (int64_t)n * p.src_bs : nullptr;
     float *gsrc = p.gsrc ? p.gsrc + (int64_t)n * p.gsrc_bs : nullptr;
     const float *go = p.gout + (int64_t)n * p.C * HW + pix;
 #pragma unroll 1
     for (int c = 0; c < p.C; ++c) {
-        float g[VEC];
-        load_vec<VEC>(go + (int64_t)c * HW, g);
+        const float g = __ldg(go + (int64_t)c * HW);
         if (p.gflow) {
             const float *s = src + (int64_t)c * HW;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                const float a = ldg_or_zero(s, t[k].o_nw), b = ldg_or_zero(s, t[k].o_ne);
-                const float cc = ldg_or_zero(s, t[k].o_sw), d = ldg_or_zero(s, t[k].o_se);
-                // d out / d ix and d out / d iy  
-                gix[k] += g[k] * ((b - a) * t[k].sy + (d - cc) * t[k].ny);
-                giy[k] += g[k] * ((cc - a) * t[k].ex + (d - b) * t[k].wx);
-                if (p.add_flow != 0.0f && c < 2) {
-                    if (c == 0) gix[k] -= p.sign * p.add_flow * g[k];
-                    else giy[k] -= p.sign * p.add_flow * g[k];
-                }
+            const float a = ldg_or_zero(s, t.o_nw), b = ldg_or_zero(s, t.o_ne);
+            const float cc = ldg_or_zero(s, t.o_sw), d = ldg_or_zero(s, t.o_se);
+            // d out / d ix and d out / d iy  
+            gix += g * ((b - a) * t.sy + (d - cc) * t.ny);
+            giy += g * ((cc - a) * t.ex + (d - b) * t.wx);
+            if (p.add_flow != 0.0f && c < 2) {
+                if (c == 0) gix -= p.sign * p.add_flow * g;
+                else giy -= p.sign * p.add_flow * g;
             }
         }
         if (gsrc) {
             float *gs = gsrc + (int64_t)c * HW;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                if (t[k].o_nw >= 0) atomicAdd(gs + t[k].o_nw, t[k].nw * g[k]);
-                if (t[k].o_ne >= 0) atomicAdd(gs + t[k].o_ne, t[k].ne * g[k]);
-                if (t[k].o_sw >= 0) atomicAdd(gs + t[k].o_sw, t[k].sw * g[k]);
-                if (t[k].o_se >= 0) atomicAdd(gs + t[k].o_se, t[k].se * g[k]);
-            }
+            if (t.o_nw >= 0) atomicAdd(gs + t.o_nw, t.nw * g);
+            if (t.o_ne >= 0) atomicAdd(gs + t.o_ne, t.ne * g);
+            if (t.o_sw >= 0) atomicAdd(gs + t.o_sw, t.sw * g);
+            if (t.o_se >= 0) atomicAdd(gs + t.o_se, t.se * g);
         }
     }
     if (p.gflow) {
-        float rx[VEC], ry[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            rx[k] = -p.sign * gix[k];   // d(ix)/d(flow_x) = -sign (the (W-1)/2 factors cancel)
-            ry[k] = -p.sign * giy[k];
-        }
         float *gf = p.gflow + (int64_t)n * 2 * HW + pix;
-        store_vec<VEC>(gf, rx);
-        store_vec<VEC>(gf + HW, ry);
+        gf[0] = -p.sign * gix;    // d(ix)/d(flow_x) = -sign (the (W-1)/2 factors cancel)
+        gf[HW] = -p.sign * giy;
     }
 }
 
@@ -220,16 +464,66 @@ extern "C" int ofb_warp_t_fwd(const float *flow, int64_t flow_bs, float flow_sig
     if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
     WarpFwdParams p{flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
                     add_flow, valid_thresh, out, valid, N, C, H, W};
-    const bool vec4 = (W % 4 == 0) && aligned16(flow) && aligned16(out) && (flow_bs % 4 == 0) &&
-                      (reinterpret_cast<uintptr_t>(valid) % 4 == 0);
-    const dim3 block(32, 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (vec4) {
-        const dim3 grid((W / 4 + 31) / 32, (H + 7) / 8, N);
-        warp_t_fwd_kernel<4><<<grid, block, 0, st>>>(p);
-    } else {
-        const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-        warp_t_fwd_kernel<1><<<grid, block, 0, st>>>(p);
+    const CoordCtx cc{{(float)(W - 1), 1.0f / (float)(W - 1)}, {(float)(H - 1), 1.0f / (float)(H - 1)}, flow_sign};
+
+    // staged (TMA) path: needs a payload, TMA-compatible pitches, and is not worth it for tiny fields
+    // Measured on B200 (profiles/): the L1-cached direct kernel beats the staged one on every flow tried (bounding-box
+    // staging over-fetches (1+g)^2 for a flow gradient g, and its load->TMA->compute phases do not overlap inside a
+    // CTA), so the staged kernel is opt-in (OFB_TMA=1) until it is software-pipelined across tiles.
+    static const bool use_tma = getenv("OFB_TMA") != nullptr;
+    bool staged = use_tma && C > 0 && W >= kTileW && H >= kTileH;
+    const int vmode = !valid ? 0 : (src_mask ? 2 : 1);
+    alignas(64) CUtensorMap mask_map;
+    alignas(64) CUtensorMap src_maps[2];          // [0]: groups of kMaxCN channels, [1]: the remainder group
+    const int groups = (C + kMaxCN - 1) / kMaxCN;
+    const int last_cn = C - (groups - 1) * kMaxCN;
+    if (staged) {
+        const uint64_t planes = (uint64_t)((src_bs == 0) ? 1 : N) * C;
+        const int first_cn = groups > 1 ? kMaxCN : C;
+        staged = make_map_3d(&src_maps[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, W, H, planes, kBoxW, kBoxH, first_cn);
+        if (staged && groups > 1 && last_cn != kMaxCN)
+            staged = make_map_3d(&src_maps[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, W, H, planes, kBoxW, kBoxH,
+                                 last_cn);
+        else
+            src_maps[1] = src_maps[0];
+        if (staged && vmode == 2)
+            staged = make_map_3d(&mask_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, src_mask, W, H,
+                                 (uint64_t)((src_mask_bs == 0) ? 1 : N), kMBoxW, kBoxH, 1);
+        else
+            mask_map = src_maps[0];
+    }
+    if (staged) {
+        const dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, N);
+        for (int g = 0; g < groups; ++g) {
+            const int cn = (g == groups - 1) ? last_cn : kMaxCN;
+            const int vm = (g == 0) ? vmode : 0;              // the validity bit is written once
+            StagedKernel k = staged_kernel(cn, vm);
+            const int smem = staged_smem_bytes(cn, vm);
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            k<<<grid, 256, smem, st>>>(p, (g == groups - 1 && groups > 1) ? src_maps[1] : src_maps[0], mask_map,
+                                       g * kMaxCN, cc);
+            OFB_CHECK_LAUNCH();
+        }
+        return 0;
+    }
+    {
+        const dim3 grid((W + 63) / 64, (H + 4 * kDirRows - 1) / (4 * kDirRows), N);
+        const bool wv = valid != nullptr;
+        switch (C) {
+            case 0: warp_t_fwd_direct_kernel<0, true><<<grid, 256, 0, st>>>(p, cc); break;
+            case 1: if (wv) warp_t_fwd_direct_kernel<1, true><<<grid, 256, 0, st>>>(p, cc);
+                    else warp_t_fwd_direct_kernel<1, false><<<grid, 256, 0, st>>>(p, cc); break;
+            case 2: if (wv) warp_t_fwd_direct_kernel<2, true><<<grid, 256, 0, st>>>(p, cc);
+                    else warp_t_fwd_direct_kernel<2, false><<<grid, 256, 0, st>>>(p, cc); break;
+            case 3: if (wv) warp_t_fwd_direct_kernel<3, true><<<grid, 256, 0, st>>>(p, cc);
+                    else warp_t_fwd_direct_kernel<3, false><<<grid, 256, 0, st>>>(p, cc); break;
+            case 4: if (wv) warp_t_fwd_direct_kernel<4, true><<<grid, 256, 0, st>>>(p, cc);
+                    else warp_t_fwd_direct_kernel<4, false><<<grid, 256, 0, st>>>(p, cc); break;
+            default: if (wv) warp_t_fwd_direct_kernel<0, true><<<grid, 256, 0, st>>>(p, cc);
+                     else warp_t_fwd_direct_kernel<0, false><<<grid, 256, 0, st>>>(p, cc); break;
+        }
     }
     OFB_CHECK_LAUNCH();
     return 0;
@@ -253,16 +547,9 @@ extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sig
         if (e != cudaSuccess) return (int)e;
     }
     WarpBwdParams p{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W};
-    const bool vec4 = (W % 4 == 0) && aligned16(flow) && aligned16(gout) && (flow_bs % 4 == 0) &&
-                      (!gflow || aligned16(gflow));
     const dim3 block(32, 8);
-    if (vec4) {
-        const dim3 grid((W / 4 + 31) / 32, (H + 7) / 8, N);
-        warp_t_bwd_kernel<4><<<grid, block, 0, st>>>(p);
-    } else {
-        const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-        warp_t_bwd_kernel<1><<<grid, block, 0, st>>>(p);
-    }
+    const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
+    warp_t_bwd_kernel<<<grid, block, 0, st>>>(p);
     OFB_CHECK_LAUNCH();
     return 0;
 }

@@ -317,3 +317,18 @@ def test_odd_width_scalar_path():
         og, vg = of().Flow(cu(flow), ref).apply(cu(img), return_valid_area=True)
         assert_close(og, oo, 'out ' + ref)
         assert_mask_equal(vg, vo, 'valid ' + ref)
+
+
+# ------------------------------------------------------------------------------------------ arithmetic self-tests
+@pytest.mark.parametrize('d', [1919, 1079, 3839, 2159, 1023, 435, 52, 36, 19, 9, 479, 199, 3, 1, 7679, 4319])
+def test_round_trip_exhaustive(d):
+    """The kernels evaluate the reference's coordinate round trip ((2c/(W-1) - 1) + 1)/2*(W-1) with a precomputed
+    reciprocal and two FMA correction steps instead of an IEEE division; the result must be bit-identical for EVERY
+    float c (all 2^32 bit patterns), because the validity masks depend on it (SURVEY.md finding 1)."""
+    import ctypes
+    from oflibpytorch_b200 import _native
+    bad = torch.zeros(1, dtype=torch.int64, device=DEV)
+    _native.check(_native.lib().ofb_selftest_div(float(d), 0, 0x80000000, ctypes.c_void_p(bad.data_ptr()),
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'selftest')
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0, '%d mismatching round trips for size-1 = %d' % (int(bad.item()), d)
