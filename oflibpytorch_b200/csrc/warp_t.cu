@@ -48,6 +48,7 @@ __device__ __forceinline__ void sample_pos(const CoordCtx &cc, float fx, float f
 
 struct PixGeom {                 // tap geometry of one output pixel
     float wnw, wne, wsw, wse;    // bilinear weights
+    float ex, wx, sy, ny;        // x1-ix, ix-x0, y1-iy, iy-y0 (used by the adjoint)
     int o;                       // yi*W + xi of the NW tap (only dereferenced under the predicates below)
     bool pnw, pne, psw, pse;     // tap inside the image (zero padding otherwise)
 };
@@ -58,6 +59,7 @@ __device__ __forceinline__ PixGeom pix_geom(float ix, float iy, int W, float wm1
     const float x0 = floorf(ix), y0 = floorf(iy);
     const float ex = __fsub_rn(__fadd_rn(x0, 1.0f), ix), wx = __fsub_rn(ix, x0);
     const float sy = __fsub_rn(__fadd_rn(y0, 1.0f), iy), ny = __fsub_rn(iy, y0);
+    g.ex = ex; g.wx = wx; g.sy = sy; g.ny = ny;
     g.wnw = __fmul_rn(ex, sy); g.wne = __fmul_rn(wx, sy);
     g.wsw = __fmul_rn(ex, ny); g.wse = __fmul_rn(wx, ny);
     // x1 = x0 + 1 in [0, W-1]  <=>  x0 in [-1, W-2]  (exact for |x0| < 2^24; beyond that everything is false)
@@ -395,54 +397,158 @@ struct WarpBwdParams {
     int N, C, H, W;
 };
 
-// v0 adjoint: gflow is a gather; gsrc is scattered with one red.global.add.f32 per tap.
-__global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p)
+// ------------------------------------------------------------------------------------------------
+// adjoint
+// ------------------------------------------------------------------------------------------------
+// gflow is a gather (payload taps x gout).  gsrc is the un-normalised splat of w*gout; issued naively that is 4*C
+// red.global.add per pixel and the L2 atomic unit becomes the limit (measured: ~0.5-0.7 T lane-ops/s).  Neighbouring
+// output pixels of a smooth flow hit neighbouring source pixels, so contributions are merged in registers first:
+//   horizontally  lane l's east taps land on lane l+1's west taps when o(l+1) == o(l)+1  -> one shuffle per value;
+//   vertically    a thread walks kBwdRows rows of one column and carries its south taps, which are the next row's
+//                 north taps when o(next) == o + W.
+// What is left is ~1 coalesced RED per pixel and channel plus sparse leftovers where the chain breaks.  Shared-memory
+// accumulation was rejected: float atomicAdd on shared memory is a CAS loop on sm_100 (ATOMS.CAST.SPIN, ~8 clk per
+// warp-op, tools/microbench.cu).
+constexpr int kBwdRows = 8;     // rows per thread; CTA tile = 64 x 32 (2 warps across x, 4 across y)
+
+// Predicated fire-and-forget reduction: `@p red.global.add.f32 [a + imm], v` -- no branch, no return value.
+// (atomicAdd() on a pointer the optimiser cannot prove global compiles to a generic ATOM with a return path.)
+template <int BYTE_OFF>
+__device__ __forceinline__ void red_add(const float *a, float v, bool pred)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.s32 q, %2, 0;\n\t"
+        "@q red.global.add.f32 [%0+%3], %1;\n\t"
+        "}" ::"l"(a), "f"(v), "r"((int)pred), "n"(BYTE_OFF));   // no "memory" clobber: gsrc is write-only here, and
+                                                                   // the clobber would pin every load behind the REDs
+}
+
+template <int CN, bool GFLOW, bool GSRC>
+__global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
+                                                         const int accumulate_gflow)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * (4 * kBwdRows) + (warp >> 1) * kBwdRows;
     const int n = blockIdx.z;
-    if (x >= p.W || y >= p.H) return;
     const int HW = p.H * p.W;
-    const int pix = y * p.W + x;
-    const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
+    const bool active = x < p.W;                       // inactive lanes still take part in the shuffles
+    const int xc = min(x, p.W - 1);
+    const int rows = min(kBwdRows, p.H - y0);          // warp-uniform
 
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
-    const float fx = __ldg(fl + pix), fy = __ldg(fl + HW + pix);
-    const float cx = __fsub_rn((float)x, __fmul_rn(p.sign, fx));
-    const float cy = __fsub_rn((float)y, __fmul_rn(p.sign, fy));
-    const Taps t = make_taps(round_trip(cx, wm1), round_trip(cy, hm1), p.H, p.W);
+    const float *src = p.src ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HW : nullptr;
+    const float *go = p.gout + ((int64_t)n * p.C + c_off) * HW;
+    float *gsrc = GSRC ? p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HW : nullptr;
+    float *gf = GFLOW ? p.gflow + (int64_t)n * 2 * HW : nullptr;
+    asm volatile("" : "+l"(fl), "+l"(src), "+l"(go), "+l"(gsrc), "+l"(gf));
 
-    float gix = 0.0f, giy = 0.0f;
-    const float *src = p.src ? p.src + (int64_t)n * p.src_bs : nullptr;
-    float *gsrc = p.gsrc ? p.gsrc + (int64_t)n * p.gsrc_bs : nullptr;
-    const float *go = p.gout + (int64_t)n * p.C * HW + pix;
-#pragma unroll 1
-    for (int c = 0; c < p.C; ++c) {
-        const float g = __ldg(go + (int64_t)c * HW);
-        if (p.gflow) {
-            const float *s = src + (int64_t)c * HW;
-            const float a = ldg_or_zero(s, t.o_nw), b = ldg_or_zero(s, t.o_ne);
-            const float cc = ldg_or_zero(s, t.o_sw), d = ldg_or_zero(s, t.o_se);
-            // d out / d ix and d out / d iy  
-            gix += g * ((b - a) * t.sy + (d - cc) * t.ny);
-            giy += g * ((cc - a) * t.ex + (d - b) * t.wx);
-            if (p.add_flow != 0.0f && c < 2) {
-                if (c == 0) gix -= p.sign * p.add_flow * g;
-                else giy -= p.sign * p.add_flow * g;
+    const float xf = (float)x, wm1 = cc.dw.d, hm1 = cc.dh.d;
+    float carry[CN];                                   // south-tap sums waiting for the next row
+    int carry_o = 0;
+    bool carry_ok = false;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) carry[c] = 0.0f;
+
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+        const int y = y0 + r;
+        const int pix = y * p.W + xc;
+        const float fx = __ldg(fl + pix), fy = __ldg(fl + (HW + pix));
+        float ix, iy;
+        sample_pos(cc, fx, fy, xf, (float)y, ix, iy);
+        PixGeom g = pix_geom(ix, iy, p.W, wm1, hm1);
+        g.pnw = g.pnw && active; g.pne = g.pne && active; g.psw = g.psw && active; g.pse = g.pse && active;
+
+        float gv[CN];
+#pragma unroll
+        for (int c = 0; c < CN; ++c) gv[c] = active ? __ldg(go + (c * HW + pix)) : 0.0f;
+
+        if (GFLOW) {
+            float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CN; ++c) {
+                const int e = c * HW + g.o;
+                float a, b, cq, d;
+                load_taps<float>(src + e, src + (e + p.W), g, a, b, cq, d);
+                // d out / d ix and d out / d iy  (SURVEY.md Appendix A.1); gradients carry a tolerance, so FMAs
+                gix = __fmaf_rn(gv[c], __fmaf_rn(b - a, g.sy, (d - cq) * g.ny), gix);
+                giy = __fmaf_rn(gv[c], __fmaf_rn(cq - a, g.ex, (d - b) * g.wx), giy);
+            }
+            // d(ix)/d(flow_x) = -sign: the (W-1)/2 and 2/(W-1) factors of the chain cancel
+            float rx = -p.sign * gix, ry = -p.sign * giy;
+            if (p.add_flow != 0.0f) {                  // out[c] = add_flow*flow[c] + ...  (combine mode 3), c < 2
+                if (c_off == 0) rx += p.add_flow * gv[0];
+                if (c_off == 0 && CN > 1) ry += p.add_flow * gv[CN > 1 ? 1 : 0];
+                if (c_off == 1) ry += p.add_flow * gv[0];
+            }
+            if (active) {
+                if (accumulate_gflow) { rx += __ldcg(gf + pix); ry += __ldcg(gf + (HW + pix)); }
+                __stcg(gf + pix, rx);
+                __stcg(gf + (HW + pix), ry);
             }
         }
-        if (gsrc) {
-            float *gs = gsrc + (int64_t)c * HW;
-            if (t.o_nw >= 0) atomicAdd(gs + t.o_nw, t.nw * g);
-            if (t.o_ne >= 0) atomicAdd(gs + t.o_ne, t.ne * g);
-            if (t.o_sw >= 0) atomicAdd(gs + t.o_sw, t.sw * g);
-            if (t.o_se >= 0) atomicAdd(gs + t.o_se, t.se * g);
+
+        if (GSRC) {
+            // ---- horizontal merge with lane-1: its east taps are my west taps when the offsets chain
+            const int prev_o = __shfl_up_sync(0xffffffffu, g.o, 1);
+            const unsigned pe = (g.pne ? 1u : 0u) | (g.pse ? 2u : 0u);
+            const unsigned prev_pe = __shfl_up_sync(0xffffffffu, pe, 1);
+            const bool chain = (lane > 0) && (prev_o + 1 == g.o);
+            const bool merge_n = chain && (prev_pe & 1u) && g.pnw;
+            const bool merge_s = chain && (prev_pe & 2u) && g.psw;
+            const unsigned bn = __ballot_sync(0xffffffffu, merge_n), bs = __ballot_sync(0xffffffffu, merge_s);
+            const bool taken_n = (lane < 31) && ((bn >> (lane + 1)) & 1u);   // my NE was absorbed by lane+1
+            const bool taken_s = (lane < 31) && ((bs >> (lane + 1)) & 1u);
+            // ---- vertical merge: the carried south taps are this row's north taps when the offsets chain
+            const bool vmerge = carry_ok && g.pnw && (carry_o == g.o);
+            const bool flush = carry_ok && !vmerge;
+            const bool east_n = g.pne && !taken_n, east_s = g.pse && !taken_s;
+#pragma unroll
+            for (int c = 0; c < CN; ++c) {
+                const float v_ne = g.pne ? g.wne * gv[c] : 0.0f, v_se = g.pse ? g.wse * gv[c] : 0.0f;
+                const float p_ne = __shfl_up_sync(0xffffffffu, v_ne, 1), p_se = __shfl_up_sync(0xffffffffu, v_se, 1);
+                float top = g.pnw ? g.wnw * gv[c] : 0.0f, bot = g.psw ? g.wsw * gv[c] : 0.0f;
+                if (merge_n) top += p_ne;
+                if (merge_s) bot += p_se;
+                const float *gs = gsrc + c * HW;
+                red_add<0>(gs + carry_o, carry[c], flush);
+                if (vmerge) top += carry[c];
+                const float *t = gs + g.o;
+                red_add<0>(t, top, g.pnw);
+                red_add<4>(t, v_ne, east_n);
+                red_add<4>(t + p.W, v_se, east_s);
+                carry[c] = bot;
+            }
+            carry_o = g.o + p.W;
+            carry_ok = g.psw;
         }
     }
-    if (p.gflow) {
-        float *gf = p.gflow + (int64_t)n * 2 * HW + pix;
-        gf[0] = -p.sign * gix;    // d(ix)/d(flow_x) = -sign (the (W-1)/2 factors cancel)
-        gf[HW] = -p.sign * giy;
+    if (GSRC && carry_ok) {
+#pragma unroll
+        for (int c = 0; c < CN; ++c) red_add<0>(gsrc + (c * HW + carry_o), carry[c], true);
+    }
+}
+
+typedef void (*BwdKernel)(const WarpBwdParams, const CoordCtx, const int, const int);
+
+template <int CN>
+static BwdKernel bwd_kernel_for(bool gflow, bool gsrc)
+{
+    if (gflow && gsrc) return warp_t_bwd_kernel<CN, true, true>;
+    if (gflow) return warp_t_bwd_kernel<CN, true, false>;
+    return warp_t_bwd_kernel<CN, false, true>;
+}
+
+static BwdKernel bwd_kernel(int cn, bool gflow, bool gsrc)
+{
+    switch (cn) {
+        case 1: return bwd_kernel_for<1>(gflow, gsrc);
+        case 2: return bwd_kernel_for<2>(gflow, gsrc);
+        case 3: return bwd_kernel_for<3>(gflow, gsrc);
+        default: return bwd_kernel_for<4>(gflow, gsrc);
     }
 }
 
@@ -547,9 +653,12 @@ extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sig
         if (e != cudaSuccess) return (int)e;
     }
     WarpBwdParams p{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W};
-    const dim3 block(32, 8);
-    const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-    warp_t_bwd_kernel<<<grid, block, 0, st>>>(p);
-    OFB_CHECK_LAUNCH();
+    const CoordCtx cc{{(float)(W - 1), 1.0f / (float)(W - 1)}, {(float)(H - 1), 1.0f / (float)(H - 1)}, flow_sign};
+    const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), N);
+    for (int c0 = 0; c0 < C; c0 += kMaxCN) {           // channel groups of <= 4; gflow accumulates across groups
+        const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
+        bwd_kernel(cn, gflow != nullptr, gsrc != nullptr)<<<grid, 256, 0, st>>>(p, cc, c0, c0 > 0 ? 1 : 0);
+        OFB_CHECK_LAUNCH();
+    }
     return 0;
 }
