@@ -1,7 +1,7 @@
 """Functional layer of the hot path: same names, arguments, return conventions and error behaviour as the
 reference's ``oflibpytorch/utils.py``, served by the sm_100a kernels.
 
-Reference map (``/root/reference/src/oflibpytorch/utils.py``):
+Reference map (the reference's ``src/oflibpytorch/utils.py``):
 
 =============================  ========================  =============================================
 here                           reference                 what changed
