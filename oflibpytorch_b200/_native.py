@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'liboflib_b200.so')
+LIB_PATH = os.environ.get('OFB_LIB_OVERRIDE') or os.path.join(_HERE, 'csrc', 'liboflib_b200.so')   # override: tuning sweeps only
 
 _lib = None
 

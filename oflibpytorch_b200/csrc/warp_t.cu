@@ -49,11 +49,12 @@ __device__ __forceinline__ void sample_pos(const CoordCtx &cc, float fx, float f
 struct PixGeom {                 // tap geometry of one output pixel
     float wnw, wne, wsw, wse;    // bilinear weights
     float ex, wx, sy, ny;        // x1-ix, ix-x0, y1-iy, iy-y0 (used by the adjoint)
-    int o;                       // yi*W + xi of the NW tap (only dereferenced under the predicates below)
+    int o;                       // yi*W + xi of the NW tap; may be negative (taps left of / above the image), so it
+                                 // is SIGN-extended when added to a pointer (only dereferenced under the predicates)
     bool pnw, pne, psw, pse;     // tap inside the image (zero padding otherwise)
 };
 
-__device__ __forceinline__ PixGeom pix_geom(float ix, float iy, int W, float wm1, float hm1)
+__device__ __forceinline__ PixGeom pix_geom(float ix, float iy, int W, int H)
 {
     PixGeom g;
     const float x0 = floorf(ix), y0 = floorf(iy);
@@ -62,27 +63,32 @@ __device__ __forceinline__ PixGeom pix_geom(float ix, float iy, int W, float wm1
     g.ex = ex; g.wx = wx; g.sy = sy; g.ny = ny;
     g.wnw = __fmul_rn(ex, sy); g.wne = __fmul_rn(wx, sy);
     g.wsw = __fmul_rn(ex, ny); g.wse = __fmul_rn(wx, ny);
-    // x1 = x0 + 1 in [0, W-1]  <=>  x0 in [-1, W-2]  (exact for |x0| < 2^24; beyond that everything is false)
-    const bool bx0 = (x0 >= 0.0f) && (x0 <= wm1), bx1 = (x0 >= -1.0f) && (x0 <= wm1 - 1.0f);
-    const bool by0 = (y0 >= 0.0f) && (y0 <= hm1), by1 = (y0 >= -1.0f) && (y0 <= hm1 - 1.0f);
+    // cvt.rmi.s32.f32 saturates (and maps NaN to 0), so far-away positions become INT_MIN/INT_MAX and fail the
+    // unsigned range tests below exactly like the reference's float comparisons x0 >= 0 && x0 <= W-1 do
+    const int xi = __float2int_rd(ix), yi = __float2int_rd(iy);
+    const bool bx0 = (unsigned)xi < (unsigned)W, bx1 = (unsigned)(xi + 1) < (unsigned)W;
+    const bool by0 = (unsigned)yi < (unsigned)H, by1 = (unsigned)(yi + 1) < (unsigned)H;
     g.pnw = bx0 && by0; g.pne = bx1 && by0; g.psw = bx0 && by1; g.pse = bx1 && by1;
-    // clamp before converting: outside [-1, size-1] every predicate is false and the offset is never used
-    const int xi = (int)fminf(fmaxf(x0, -1.0f), wm1), yi = (int)fminf(fmaxf(y0, -1.0f), hm1);
-    g.o = yi * W + xi;
+    g.o = (int)((unsigned)yi * (unsigned)W + (unsigned)xi);   // wraps harmlessly for saturated (far away) positions
     return g;
 }
 
 // The four taps of one plane.  `north` points at the NW tap, `south` one image row below; each is ONE 64-bit
 // address, the east taps are immediate offsets.  Out-of-image taps are not loaded and read as zero.
-template <typename T>
+// ALL_IN: warp-uniform fast path, every tap of every lane is inside the image -> no predication, no zero-init.
+template <bool ALL_IN, typename T>
 __device__ __forceinline__ void load_taps(const T *__restrict__ north, const T *__restrict__ south, const PixGeom &g,
                                           T &a, T &b, T &c, T &d)
 {
-    a = b = c = d = T(0);
-    if (g.pnw) a = __ldg(north);
-    if (g.pne) b = __ldg(north + 1);
-    if (g.psw) c = __ldg(south);
-    if (g.pse) d = __ldg(south + 1);
+    if (ALL_IN) {
+        a = __ldg(north); b = __ldg(north + 1); c = __ldg(south); d = __ldg(south + 1);
+    } else {
+        a = b = c = d = T(0);
+        if (g.pnw) a = __ldg(north);
+        if (g.pne) b = __ldg(north + 1);
+        if (g.psw) c = __ldg(south);
+        if (g.pse) d = __ldg(south + 1);
+    }
 }
 
 __device__ __forceinline__ float blend4(const PixGeom &g, float a, float b, float c, float d)
@@ -92,6 +98,9 @@ __device__ __forceinline__ float blend4(const PixGeom &g, float a, float b, floa
     r = __fmaf_rn(c, g.wsw, r);
     return __fmaf_rn(d, g.wse, r);
 }
+
+// 0/1 mask byte -> 0.0f/1.0f without the conversion pipe: 1 * 0x3f800000 is the bit pattern of 1.0f
+__device__ __forceinline__ float mask_to_float(uint8_t m) { return __uint_as_float((unsigned)m * 0x3f800000u); }
 
 // Per-thread base pointers of one batch item (computed once; everything below is 32-bit offsets from them).
 struct ItemPtrs {
@@ -104,17 +113,19 @@ struct ItemPtrs {
 
 // One output pixel through global memory: channels [0, CN) (CN = 0: cn_rt channels, runtime loop).
 // pix = y*W + x of the output pixel; c_first = absolute index of channel 0 (for add_flow).
-template <int CN, bool WANT_VALID>
+template <int CN, bool WANT_VALID, bool ALL_IN>
 __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const ItemPtrs &ip, const PixGeom &g,
                                                   int pix, float fx, float fy, int c_first, int cn_rt)
 {
-    const int HW = p.H * p.W;
+    const int HW = p.H * p.W, W = p.W;
     if (WANT_VALID) {
         float a, b, c, d;
         if (ip.smask) {
             uint8_t ua, ub, uc, ud;
-            load_taps<uint8_t>(ip.smask + g.o, ip.smask + (g.o + p.W), g, ua, ub, uc, ud);
-            a = ua ? 1.0f : 0.0f; b = ub ? 1.0f : 0.0f; c = uc ? 1.0f : 0.0f; d = ud ? 1.0f : 0.0f;
+            load_taps<ALL_IN, uint8_t>(ip.smask + g.o, ip.smask + (g.o + W), g, ua, ub, uc, ud);
+            a = mask_to_float(ua); b = mask_to_float(ub); c = mask_to_float(uc); d = mask_to_float(ud);
+        } else if (ALL_IN) {
+            a = b = c = d = 1.0f;
         } else {
             a = g.pnw ? 1.0f : 0.0f; b = g.pne ? 1.0f : 0.0f; c = g.psw ? 1.0f : 0.0f; d = g.pse ? 1.0f : 0.0f;
         }
@@ -127,7 +138,7 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
         for (int c = 0; c < CN; ++c) {
             const int e = c * HW + g.o;                                              // one int add per plane
             float a, b, cc, d;
-            load_taps<float>(ip.src + e, ip.src + (e + p.W), g, a, b, cc, d);
+            load_taps<ALL_IN, float>(ip.src + e, ip.src + (e + W), g, a, b, cc, d);
             float r = blend4(g, a, b, cc, d);
             if (p.add_flow != 0.0f && c_first + c < 2)                               // flow_class.py:1804,1808
                 r = __fadd_rn(__fmul_rn(p.add_flow, (c_first + c) == 0 ? fx : fy), r);
@@ -138,13 +149,27 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
         for (int c = 0; c < cn_rt; ++c) {
             const int64_t e = (int64_t)c * HW + g.o;
             float a, b, cc, d;
-            load_taps<float>(ip.src + e, ip.src + (e + p.W), g, a, b, cc, d);
+            load_taps<ALL_IN, float>(ip.src + e, ip.src + (e + W), g, a, b, cc, d);
             float r = blend4(g, a, b, cc, d);
             if (p.add_flow != 0.0f && c_first + c < 2)
                 r = __fadd_rn(__fmul_rn(p.add_flow, (c_first + c) == 0 ? fx : fy), r);
             ip.out[(int64_t)c * HW + pix] = r;
         }
     }
+}
+
+// dispatch on the warp-uniform "every tap of every lane is inside the image" predicate (true for all but the
+// warps that sample near the image border)
+template <int CN, bool WANT_VALID>
+__device__ __forceinline__ void warp_pixel(const WarpFwdParams &p, const ItemPtrs &ip, const PixGeom &g,
+                                           int pix, float fx, float fy, int c_first, int cn_rt)
+{
+#ifdef OFB_ALLIN_FASTPATH
+    if (__all_sync(__activemask(), g.pnw && g.pne && g.psw && g.pse))
+        warp_pixel_direct<CN, WANT_VALID, true>(p, ip, g, pix, fx, fy, c_first, cn_rt);
+    else
+#endif
+        warp_pixel_direct<CN, WANT_VALID, false>(p, ip, g, pix, fx, fy, c_first, cn_rt);
 }
 
 __device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, int n, int c_off)
@@ -181,7 +206,7 @@ __global__ void __launch_bounds__(256) warp_t_fwd_direct_kernel(const WarpFwdPar
         fx[r] = __ldg(fl + q);
         fy[r] = __ldg(fl + (HW + q));
     }
-    const float xf = (float)x, wm1 = cc.dw.d, hm1 = cc.dh.d;
+    const float xf = (float)x;
     const ItemPtrs ip = item_ptrs(p, n, 0);
     const int rows = min(kDirRows, p.H - y0);
 #pragma unroll
@@ -189,8 +214,8 @@ __global__ void __launch_bounds__(256) warp_t_fwd_direct_kernel(const WarpFwdPar
         if (r >= rows) break;
         float ix, iy;
         sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r), ix, iy);
-        const PixGeom g = pix_geom(ix, iy, p.W, wm1, hm1);
-        warp_pixel_direct<CN, WANT_VALID>(p, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C);
+        const PixGeom g = pix_geom(ix, iy, p.W, p.H);
+        warp_pixel<CN, WANT_VALID>(p, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C);
     }
 }
 
@@ -308,8 +333,8 @@ __global__ void __launch_bounds__(256, 3) warp_t_fwd_staged_kernel(const WarpFwd
             const float fx = __ldg(fl + y * p.W), fy = __ldg(fl + HW + y * p.W);
             float jx, jy;
             sample_pos(cc, fx, fy, xf, (float)y, jx, jy);
-            const PixGeom g = pix_geom(jx, jy, p.W, cc.dw.d, cc.dh.d);
-            warp_pixel_direct<CN, VMODE != 0>(p, ip, g, y * p.W + x, fx, fy, c_off, CN);
+            const PixGeom g = pix_geom(jx, jy, p.W, p.H);
+            warp_pixel_direct<CN, VMODE != 0, false>(p, ip, g, y * p.W + x, fx, fy, c_off, CN);
         }
         return;
     }
@@ -409,7 +434,13 @@ struct WarpBwdParams {
 // What is left is ~1 coalesced RED per pixel and channel plus sparse leftovers where the chain breaks.  Shared-memory
 // accumulation was rejected: float atomicAdd on shared memory is a CAS loop on sm_100 (ATOMS.CAST.SPIN, ~8 clk per
 // warp-op, tools/microbench.cu).
-constexpr int kBwdRows = 8;     // rows per thread; CTA tile = 64 x 32 (2 warps across x, 4 across y)
+#ifndef OFB_BWD_ROWS
+#define OFB_BWD_ROWS 8
+#endif
+#ifndef OFB_BWD_MINB
+#define OFB_BWD_MINB 4
+#endif
+constexpr int kBwdRows = OFB_BWD_ROWS;     // rows per thread; CTA tile = 64 x 4*rows (2 warps across x, 4 across y)
 
 // Predicated fire-and-forget reduction: `@p red.global.add.f32 [a + imm], v` -- no branch, no return value.
 // (atomicAdd() on a pointer the optimiser cannot prove global compiles to a generic ATOM with a return path.)
@@ -426,7 +457,7 @@ __device__ __forceinline__ void red_add(const float *a, float v, bool pred)
 }
 
 template <int CN, bool GFLOW, bool GSRC>
-__global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
+__global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
                                                          const int accumulate_gflow)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -445,7 +476,7 @@ __global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p, 
     float *gf = GFLOW ? p.gflow + (int64_t)n * 2 * HW : nullptr;
     asm volatile("" : "+l"(fl), "+l"(src), "+l"(go), "+l"(gsrc), "+l"(gf));
 
-    const float xf = (float)x, wm1 = cc.dw.d, hm1 = cc.dh.d;
+    const float xf = (float)x;
     float carry[CN];                                   // south-tap sums waiting for the next row
     int carry_o = 0;
     bool carry_ok = false;
@@ -459,7 +490,7 @@ __global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p, 
         const float fx = __ldg(fl + pix), fy = __ldg(fl + (HW + pix));
         float ix, iy;
         sample_pos(cc, fx, fy, xf, (float)y, ix, iy);
-        PixGeom g = pix_geom(ix, iy, p.W, wm1, hm1);
+        PixGeom g = pix_geom(ix, iy, p.W, p.H);
         g.pnw = g.pnw && active; g.pne = g.pne && active; g.psw = g.psw && active; g.pse = g.pse && active;
 
         float gv[CN];
@@ -472,7 +503,7 @@ __global__ void __launch_bounds__(256) warp_t_bwd_kernel(const WarpBwdParams p, 
             for (int c = 0; c < CN; ++c) {
                 const int e = c * HW + g.o;
                 float a, b, cq, d;
-                load_taps<float>(src + e, src + (e + p.W), g, a, b, cq, d);
+                load_taps<false, float>(src + e, src + (e + p.W), g, a, b, cq, d);
                 // d out / d ix and d out / d iy  (SURVEY.md Appendix A.1); gradients carry a tolerance, so FMAs
                 gix = __fmaf_rn(gv[c], __fmaf_rn(b - a, g.sy, (d - cq) * g.ny), gix);
                 giy = __fmaf_rn(gv[c], __fmaf_rn(cq - a, g.ex, (d - b) * g.wx), giy);
@@ -647,18 +678,38 @@ extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sig
     if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!gflow && !gsrc) return 0;
-    if (gsrc) {
-        const int64_t items = (gsrc_bs == 0) ? 1 : N;
-        cudaError_t e = cudaMemsetAsync(gsrc, 0, sizeof(float) * (size_t)items * C * H * W, st);
+    const CoordCtx cc{{(float)(W - 1), 1.0f / (float)(W - 1)}, {(float)(H - 1), 1.0f / (float)(H - 1)}, flow_sign};
+    // Optional L2-resident accumulation (OFB_BWD_CHUNK_MB > 0): walk the batch in chunks whose gradient image fits the
+    // L2, zero-filling each chunk right before its kernel so the REDs hit L2-resident lines (-24 B/pixel of DRAM
+    // traffic).  Measured on B200: a LOSS as separate launches (1.47 -> 1.58/1.75/1.88 ms at 96/48/24 MB chunks,
+    // tails and launch gaps dominate), hence off by default; it needs the zero-fill fused into one persistent kernel.
+    static const long chunk_mb = getenv("OFB_BWD_CHUNK_MB") ? atol(getenv("OFB_BWD_CHUNK_MB")) : 0;
+    const int64_t item_bytes = (int64_t)C * H * W * 4;
+    int chunk = N;
+    if (gsrc && gsrc_bs != 0 && chunk_mb > 0) {
+        chunk = (int)((chunk_mb << 20) / item_bytes);
+        if (chunk < 1) chunk = 1;
+        if (chunk > N) chunk = N;
+    }
+    if (gsrc && gsrc_bs == 0) {                          // broadcast payload: one image accumulates the whole batch
+        cudaError_t e = cudaMemsetAsync(gsrc, 0, (size_t)item_bytes, st);
         if (e != cudaSuccess) return (int)e;
     }
-    WarpBwdParams p{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W};
-    const CoordCtx cc{{(float)(W - 1), 1.0f / (float)(W - 1)}, {(float)(H - 1), 1.0f / (float)(H - 1)}, flow_sign};
-    const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), N);
-    for (int c0 = 0; c0 < C; c0 += kMaxCN) {           // channel groups of <= 4; gflow accumulates across groups
-        const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
-        bwd_kernel(cn, gflow != nullptr, gsrc != nullptr)<<<grid, 256, 0, st>>>(p, cc, c0, c0 > 0 ? 1 : 0);
-        OFB_CHECK_LAUNCH();
+    for (int n0 = 0; n0 < N; n0 += chunk) {
+        const int nn = (N - n0 < chunk) ? (N - n0) : chunk;
+        if (gsrc && gsrc_bs != 0) {
+            cudaError_t e = cudaMemsetAsync(gsrc + (int64_t)n0 * gsrc_bs, 0, (size_t)item_bytes * nn, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+        WarpBwdParams p{flow + (int64_t)n0 * flow_bs, flow_bs, flow_sign, src ? src + (int64_t)n0 * src_bs : nullptr, src_bs,
+                        gout + (int64_t)n0 * C * H * W, add_flow, gflow ? gflow + (int64_t)n0 * 2 * H * W : nullptr,
+                        gsrc ? gsrc + (int64_t)n0 * gsrc_bs : nullptr, gsrc_bs, nn, C, H, W};
+        const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), nn);
+        for (int c0 = 0; c0 < C; c0 += kMaxCN) {       // channel groups of <= 4; gflow accumulates across groups
+            const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
+            bwd_kernel(cn, gflow != nullptr, gsrc != nullptr)<<<grid, 256, 0, st>>>(p, cc, c0, c0 > 0 ? 1 : 0);
+            OFB_CHECK_LAUNCH();
+        }
     }
     return 0;
 }

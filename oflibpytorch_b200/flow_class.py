@@ -1,8 +1,8 @@
 """The ``Flow`` container and its hot-path methods, API-compatible with the reference's
 ``oflibpytorch/flow_class.py`` for: construction and properties (flow_class.py:37-236), arithmetic
 (:450-692), ``pad``/``unpad`` (:715-753), ``apply`` (:755-959), ``switch_ref`` (:1022-1062), ``invert``
-(:1064-1086), ``valid_target``/``valid_source`` (:1088-1172), ``is_zero`` (:1226-1244) and ``combine_with``
-(:1648-1810).
+(:1064-1086), ``valid_target``/``valid_source`` (:1088-1172), ``is_zero`` (:1226-1244), ``combine_with``
+(:1648-1810) and ``combine`` (:1812-1939).
 
 What is different from the reference, by design:
 
@@ -529,6 +529,55 @@ class Flow(object):
             flow_inv_t = flow.invert('t')
             return flow - (flow_inv_t + flow_inv_t.apply(self.switch_ref())).apply(self)
         return self.invert().apply(flow - self)                      # flow_class.py:1763
+
+    def combine(self, other: FlowAlias, mode: int, ref: str = None) -> FlowAlias:
+        """flow_1 (+) flow_2 = flow_3 for flows of ANY reference, result in reference `ref` (reference
+        flow_class.py:1812-1939; the successor of `combine_with`).  Pure composition of apply / invert / switch_ref,
+        so it runs entirely on the fused kernels.
+
+        mode 1: self = flow_2, other = flow_3, result flow_1;  mode 2: self = flow_1, other = flow_3, result flow_2;
+        mode 3: self = flow_1, other = flow_2, result flow_3."""
+        if not isinstance(other, Flow):
+            raise TypeError("Error combining flows: Flow need to be of type 'Flow'")
+        if self.shape != other.shape:
+            raise ValueError("Error combining flows: Flow fields need to have the same shape, including batch size")
+        if self._device != other._device:
+            other = other.to_device(self._device)
+        if mode not in [1, 2, 3]:
+            raise ValueError("Error combining flows: Mode needs to be 1, 2 or 3")
+        ref = self._ref if ref is None else get_valid_ref(ref)
+
+        # "times" 0,1,2 = the three images the flows connect: flow_1: 0->1, flow_2: 1->2, flow_3: 0->2
+        span = {1: (0, 1), 2: (1, 2), 3: (0, 2)}                     # flow index -> (source time, target time)
+        sign = [[0, 1, 1], [-1, 0, 1], [-1, -1, 0]]                  # direction of travel between two times
+        unknown = mode
+        known_self, known_other = {1: (2, 3), 2: (1, 3), 3: (1, 2)}[mode]
+        s_time, t_time = span[unknown]
+        goal = s_time if ref == 's' else t_time                      # time frame the result must live in
+        rest = ({0, 1, 2} - {s_time, t_time}).pop()                  # the third time
+
+        def frame(flow, idx):                                        # time frame a flow's vectors are anchored in
+            return span[idx][0] if flow._ref == 's' else span[idx][1]
+
+        # the "close" input touches the goal time, the "far" one does not
+        if (mode == 1 and goal == s_time) or (mode in (2, 3) and goal == t_time):
+            close, close_idx, far, far_idx = other, known_other, self, known_self
+        else:
+            close, close_idx, far, far_idx = self, known_self, other, known_other
+        close_frame, far_frame = frame(close, close_idx), frame(far, far_idx)
+
+        if far_frame in (s_time, t_time):                            # anchored "around the corner": bring it adjacent
+            far = far.switch_ref()
+        if close_frame == goal:                                      # move far from the third time to the goal time
+            far = close.apply(far) if sign[rest][goal] == 1 else close.invert(ref='t').apply(far)
+        if goal == t_time:
+            result = far * sign[s_time][rest] + close * sign[rest][t_time]
+        else:
+            result = close * sign[s_time][rest] + far * sign[rest][t_time]
+        if close_frame != goal:                                      # the sum lives at the third time: move it
+            result = close.apply(result) if sign[rest][goal] == 1 else close.invert(ref='s').apply(result)
+        result._ref = ref
+        return result
 
     def _fused_warp_add(self, payload: FlowAlias, sign: float) -> FlowAlias:
         """v_self + W(sign*v_self, [v_payload | m_payload]) with mask (theta(mask channel) & m_self).

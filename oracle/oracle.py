@@ -246,6 +246,9 @@ class OFlow:
     def __neg__(self):
         return OFlow(self.vecs * -1.0, self.ref, self.mask)            # flow_class.py:692,549
 
+    def __mul__(self, k):
+        return OFlow(self.vecs * float(k), self.ref, self.mask)        # flow_class.py:549
+
     def __add__(self, o):
         return OFlow(self.vecs + o.vecs, self.ref, self.mask & o.mask)  # flow_class.py:483-488
 
@@ -392,6 +395,35 @@ class OFlow:
         if s:
             return self + self.invert(ref='t').apply(flow)
         return flow + flow.apply(self)
+
+
+def combine(a: OFlow, b: OFlow, mode: int, ref=None) -> OFlow:
+    """flow_class.py:1812-1939, restated with explicit time frames (0, 1, 2 = the three images)."""
+    ref = a.ref if ref is None else ref
+    span = {1: (0, 1), 2: (1, 2), 3: (0, 2)}
+    sign = [[0, 1, 1], [-1, 0, 1], [-1, -1, 0]]
+    ia, ib = {1: (2, 3), 2: (1, 3), 3: (1, 2)}[mode]
+    s_time, t_time = span[mode]
+    goal = s_time if ref == 's' else t_time
+    rest = ({0, 1, 2} - {s_time, t_time}).pop()
+    anchor = lambda f, i: span[i][0] if f.ref == 's' else span[i][1]   # noqa: E731
+    if (mode == 1 and goal == s_time) or (mode in (2, 3) and goal == t_time):
+        close, ic, far, jf = b, ib, a, ia
+    else:
+        close, ic, far, jf = a, ia, b, ib
+    cf, ff = anchor(close, ic), anchor(far, jf)
+    if ff in (s_time, t_time):
+        far = far.switch_ref()
+    if cf == goal:
+        far = close.apply(far) if sign[rest][goal] == 1 else close.invert('t').apply(far)
+    if goal == t_time:
+        res = far * sign[s_time][rest] + close * sign[rest][t_time]
+    else:
+        res = close * sign[s_time][rest] + far * sign[rest][t_time]
+    if cf != goal:
+        res = close.apply(res) if sign[rest][goal] == 1 else close.invert('s').apply(res)
+    res.ref = ref
+    return res
 
 
 # ----------------------------------------------------------------------------------------------

@@ -52,5 +52,24 @@ for ref in 'st':
     for mode, (a, b) in {1: (f2, f3), 2: (f1, f3), 3: (f1, f2)}.items():
         r = a.combine_with(b, mode)
         out['cmb_%s_%d_vecs' % (ref, mode)], out['cmb_%s_%d_mask' % (ref, mode)] = r.vecs.numpy(), r.mask.numpy()
+# flow_class.py:1812-1939 Flow.combine: every mode x ref(self) x ref(other) x ref(result), masked, random smooth flows
+import torch.nn.functional as F  # noqa: E402
+g = torch.Generator().manual_seed(77)
+def smooth(seed):
+    gg = torch.Generator().manual_seed(seed)
+    lo = torch.randn(2, 2, 4, 5, generator=gg) * 2.5
+    return F.interpolate(lo, size=(30, 44), mode='bicubic', align_corners=True).contiguous()
+ca, cb = smooth(1), smooth(2)
+ma = torch.rand(2, 30, 44, generator=g) > 0.06
+mb = torch.rand(2, 30, 44, generator=g) > 0.06
+out['cmbx_a'], out['cmbx_b'], out['cmbx_ma'], out['cmbx_mb'] = ca.numpy(), cb.numpy(), ma.numpy(), mb.numpy()
+for mode in (1, 2, 3):
+    for ra in 'st':
+        for rb in 'st':
+            for ro in 'st':
+                r = of.Flow(ca, ra, ma).combine(of.Flow(cb, rb, mb), mode, ro)
+                k = 'cmbx_%d%s%s%s' % (mode, ra, rb, ro)
+                out[k + '_v'], out[k + '_m'] = r.vecs.numpy(), r.mask.numpy()
+                assert r.ref == ro
 np.savez_compressed(os.path.join(HERE, 'kats_v1.npz'), **out)
 print('wrote', len(out), 'arrays', os.path.getsize(os.path.join(HERE, 'kats_v1.npz')) // 1024, 'KiB')

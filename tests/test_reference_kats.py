@@ -23,6 +23,9 @@ class OracleImpl:
         from oracle import oracle as orc
         self.o = orc
 
+    def combine(self, a, b, mode, ref):
+        return self.o.combine(a, b, mode, ref)
+
     def flow(self, vecs, ref, mask=None):
         return self.o.OFlow(vecs, ref, mask)
 
@@ -39,6 +42,9 @@ class CudaImpl:
     def __init__(self):
         import oflibpytorch_b200 as of
         self.of = of
+
+    def combine(self, a, b, mode, ref):
+        return a.combine(b, mode, ref)
 
     def flow(self, vecs, ref, mask=None):
         return self.of.Flow(vecs.cuda(), ref, None if mask is None else torch.as_tensor(mask).cuda())
@@ -145,3 +151,25 @@ def test_combine_analytic(impl_cls, ref, mode):
     assert m.sum() > 0.4 * m.size
     err = np.abs(vecs[0].numpy() - f[want][0].numpy())[:, m]
     assert float(err.max()) < 0.8
+
+
+@pytest.mark.parametrize('impl_cls', IMPLS)
+@pytest.mark.parametrize('mode', [1, 2, 3])
+def test_combine_general_refs(impl_cls, mode):
+    """Flow.combine (reference flow_class.py:1812-1939) for every combination of input and output
+    references, against the reference's own results (bit-exact masks; vectors bit-exact for the oracle, within the
+    port tolerance for the CUDA path)."""
+    im = impl_cls()
+    a, b, ma, mb = T('cmbx_a'), T('cmbx_b'), T('cmbx_ma'), T('cmbx_mb')
+    for ra in 'st':
+        for rb in 'st':
+            for ro in 'st':
+                r = im.combine(im.flow(a, ra, ma), im.flow(b, rb, mb), mode, ro)
+                k = 'cmbx_%d%s%s%s' % (mode, ra, rb, ro)
+                assert r.ref == ro
+                np.testing.assert_array_equal(r.mask.cpu().numpy(), KATS[k + '_m'], err_msg=k)
+                if im.dev == 'cpu':
+                    np.testing.assert_array_equal(r.vecs.detach().numpy(), KATS[k + '_v'], err_msg=k)
+                else:
+                    np.testing.assert_allclose(r.vecs.detach().cpu().numpy(), KATS[k + '_v'], rtol=1e-4, atol=1e-3,
+                                               err_msg=k)
