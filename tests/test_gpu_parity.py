@@ -332,3 +332,27 @@ def test_round_trip_exhaustive(d):
                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'selftest')
     torch.cuda.synchronize()
     assert int(bad.item()) == 0, '%d mismatching round trips for size-1 = %d' % (int(bad.item()), d)
+
+
+def test_host_pipeline_matches_direct_call():
+    """oflibpytorch_b200.streaming.HostWarpPipeline (chunked, three streams) == one direct call on the whole batch."""
+    from oflibpytorch_b200.streaming import HostWarpPipeline
+    n, c, h, w = 5, 3, 72, 96                        # 5 items in chunks of 2: ragged last chunk
+    flow = smooth_flow(n, h, w, 4.0, 800)
+    img = torch.rand(n, c, h, w, generator=gen(801))
+    gout = torch.rand(n, c, h, w, generator=gen(802))
+    fmask, tmask = holed_mask(n, h, w, 803), holed_mask(n, h, w, 804)
+    pipe = HostWarpPipeline(torch.device('cuda', 0), chunk=2)
+    pin = [t.pin_memory() for t in (flow, img, fmask, tmask, gout)]
+    for _ in range(2):                               # second run reuses the device buffers
+        out_h, valid_h, gf_h, gi_h = pipe.run(pin[0], pin[1], 't', pin[2], pin[3], pin[4])
+        torch.cuda.synchronize()
+    fg, ig = cu(flow).requires_grad_(), cu(img).requires_grad_()
+    og, vg = of().Flow(fg, 't', cu(fmask)).apply(ig, cu(tmask), return_valid_area=True)
+    og.backward(cu(gout))
+    assert bit_equal(out_h, og) and torch.equal(valid_h, vg.cpu())
+    assert_grad_close(gf_h, fg.grad, 'gflow')
+    assert_grad_close(gi_h, ig.grad, 'gimg')
+    out2, valid2, g1, g2 = pipe.run(pin[0], pin[1], 't', pin[2], pin[3])      # forward only
+    torch.cuda.synchronize()
+    assert g1 is None and g2 is None and bit_equal(out2, og) and torch.equal(valid2, vg.cpu())
