@@ -95,6 +95,9 @@ int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sign,
                    float *gflow, float *gsrc, int64_t gsrc_bs,
                    int N, int C, int H, int W, void *stream);
 
+/* Workspace (in floats) ofb_splat_s_fwd needs for this problem; has_data_mask != 0 iff data_mask will be given. */
+int64_t ofb_splat_s_workspace(int N, int C, int H, int W, int has_data_mask);
+
 /* S -- normalised bilinear forward splat.  Replaces get_flow_endpoints (utils.py:1045-1058),
  * grid_from_unstructured_data (utils.py:1061-1154) and apply_s_flow (utils.py:1157-1205), and, with
  * `data_mask`/`valid`, the mask tracking of Flow.apply for 's' flows (flow_class.py:880-898,922).
@@ -106,7 +109,7 @@ int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sign,
  *   flow_mask (N|1, H, W) sources to ignore (apply_s_flow's `mask`); NULL = all true
  *   occlude_zero  != 0: sources with |f0|<1e-3 and |f1|<1e-3 are left out and filled back in where
  *                 nothing landed (utils.py:1190-1203); requires relative != 0
- *   acc       workspace of N*(C+2)*H*W floats, zero-filled by the call
+ *   acc       workspace of acc_floats floats (ask ofb_splat_s_workspace), zero-filled and reused by the call
  *   out (N,C,H,W); density (N,H,W) NULL ok; warped_mask (N,H,W) = density > 0, NULL ok;
  *   unocc (N,H,W) = pixels filled back in by the occlusion rule (needed by the adjoint), NULL ok;
  *   valid (N,H,W) by rule valid_mode, NULL ok. */
@@ -114,7 +117,7 @@ int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_bs, int rela
                     const float *data, int64_t data_bs,
                     const uint8_t *data_mask, int64_t data_mask_bs,
                     const uint8_t *flow_mask, int64_t flow_mask_bs,
-                    int occlude_zero, float *acc,
+                    int occlude_zero, float *acc, int64_t acc_floats,
                     float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
                     uint8_t *valid, int valid_mode,
                     int N, int C, int H, int W, void *stream);
@@ -123,14 +126,20 @@ int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_bs, int rela
  *   out, density, unocc   the forward results (out BEFORE any dtype rounding; unocc NULL = none)
  *   gout (N,C,H,W); gdensity (N,H,W) NULL = zero
  *   gcx, gcy       (N,H,W) planes with batch stride gcoord_bs (the two planes of gflow), NULL ok (both)
- *   gdata          (N,C,H,W), NULL ok */
+ *   gdata          (N,C,H,W), NULL ok
+ *   work           scratch of work_floats floats (ofb_splat_s_bwd_workspace), NULL ok */
 int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
                     const float *data, int64_t data_bs,
                     const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
                     const float *out, const float *density, const uint8_t *unocc,
                     const float *gout, const float *gdensity,
                     float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                    float *work, int64_t work_floats,
                     int N, int C, int H, int W, void *stream);
+
+/* Workspace (in floats) ofb_splat_s_bwd wants for its vector-gather path; 0 = none.  `work` may be NULL (then the
+ * generic scalar-gather kernel runs). */
+int64_t ofb_splat_s_bwd_workspace(int N, int C, int H, int W);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,8 @@ _lib.define("warp_t_fwd(Tensor flow, float sign, Tensor? src, Tensor? src_mask, 
 _lib.define("warp_t_bwd(Tensor flow, float sign, Tensor src, Tensor gout, float add_flow, "
             "bool need_gflow, bool need_gsrc) -> (Tensor, Tensor)")
 _lib.define("splat_s_fwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor? data, Tensor? data_mask, "
-            "Tensor? flow_mask, bool occlude_zero, int valid_mode) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+            "Tensor? flow_mask, bool occlude_zero, int valid_mode, bool want_aux) -> "
+            "(Tensor, Tensor, Tensor, Tensor, Tensor)")
 _lib.define("splat_s_bwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor data, Tensor? flow_mask, "
             "bool occlude_zero, Tensor out, Tensor density, Tensor? unocc, Tensor? gout, Tensor? gdensity, "
             "bool need_gcoord, bool need_gdata) -> (Tensor, Tensor)")
@@ -163,7 +164,7 @@ def _coord_planes(cx: torch.Tensor, cy: torch.Tensor):
     return cx, cy
 
 
-def _splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask, occlude_zero, valid_mode):
+def _splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask, occlude_zero, valid_mode, want_aux):
     require_cuda(cx, "flow")
     cx, cy = _coord_planes(cx, cy)
     data = None if data is None else _f32c(data)
@@ -175,18 +176,21 @@ def _splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask, occlude_zer
     dev = cx.device
     want_valid = valid_mode != VALID_NONE
     with torch.cuda.device(dev):
-        acc = torch.empty((n, c + 2, h, w), dtype=torch.float32, device=dev)
+        acc_floats = int(_native.lib().ofb_splat_s_workspace(n, c, h, w, int(data_mask is not None)))
+        acc = torch.empty((acc_floats,), dtype=torch.float32, device=dev)
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
-        density = torch.empty((n, h, w), dtype=torch.float32, device=dev)
-        wmask = torch.empty((n, h, w), dtype=torch.bool, device=dev)
-        unocc = torch.empty((n, h, w) if occlude_zero else (0,), dtype=torch.bool, device=dev)
+        # density / warped mask / un-occlusion mask are only materialised when the caller or the adjoint needs them
+        density = torch.empty((n, h, w) if want_aux else (0,), dtype=torch.float32, device=dev)
+        wmask = torch.empty((n, h, w) if want_aux else (0,), dtype=torch.bool, device=dev)
+        unocc = torch.empty((n, h, w) if (occlude_zero and want_aux) else (0,), dtype=torch.bool, device=dev)
         valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
         _call("ofb_splat_s_fwd", 
             _p(cx), _p(cy), 0 if (cx.shape[0] == 1 and n > 1) else cx.stride(0), int(relative), sign,
             _p(data) if c else None, _bs(data, n, c * hw),
             _p(data_mask), _bs(data_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
-            int(occlude_zero), _p(acc), _p(out) if c else None, _p(density), _p(wmask),
-            _p(unocc) if occlude_zero else None, _p(valid) if want_valid else None, valid_mode,
+            int(occlude_zero), _p(acc), acc_floats, _p(out) if c else None, _p(density) if want_aux else None,
+            _p(wmask) if want_aux else None, _p(unocc) if (occlude_zero and want_aux) else None,
+            _p(valid) if want_valid else None, valid_mode,
             n, c, h, w, _stream())
     return out, density, wmask, unocc, valid
 
@@ -205,6 +209,8 @@ def _splat_s_bwd(cx, cy, relative, sign, data, flow_mask, occlude_zero, out, den
         gdensity = None if gdensity is None else _f32c(gdensity)
         gcoord = torch.empty((n, 2, h, w) if need_gcoord else (0,), dtype=torch.float32, device=dev)
         gdata = torch.empty((n, c, h, w) if need_gdata else (0,), dtype=torch.float32, device=dev)
+        work_floats = int(_native.lib().ofb_splat_s_bwd_workspace(n, c, h, w))
+        work = torch.empty((work_floats,), dtype=torch.float32, device=dev) if work_floats else None
         gcx = ctypes.c_void_p(gcoord.data_ptr()) if need_gcoord else None
         gcy = ctypes.c_void_p(gcoord.data_ptr() + 4 * hw) if need_gcoord else None
         _call("ofb_splat_s_bwd", 
@@ -212,7 +218,7 @@ def _splat_s_bwd(cx, cy, relative, sign, data, flow_mask, occlude_zero, out, den
             _p(data), _bs(data, n, c * hw), _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero),
             _p(out), _p(density), _p(unocc) if (unocc is not None and unocc.numel()) else None,
             _p(gout), _p(gdensity), gcx, gcy, 2 * hw, _p(gdata) if need_gdata else None,
-            n, c, h, w, _stream())
+            _p(work), work_floats, n, c, h, w, _stream())
     return gcoord, gdata
 
 
@@ -264,7 +270,7 @@ class _SplatS(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cx, cy, data, data_mask, flow_mask, relative, sign, occlude_zero, valid_mode):
         out, density, wmask, unocc, valid = _ops.splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask,
-                                                             occlude_zero, valid_mode)
+                                                             occlude_zero, valid_mode, True)
         ctx.save_for_backward(cx, cy, data, flow_mask, out, density, unocc)
         ctx.relative, ctx.sign, ctx.occlude_zero = relative, sign, occlude_zero
         ctx.mark_non_differentiable(wmask, valid)
@@ -302,12 +308,19 @@ def warp_t(flow, src, src_mask=None, flow_mask=None, sign=1.0, add_flow=0.0, thr
                         bool(want_valid))
 
 
-def splat_flow(flow, data, data_mask=None, flow_mask=None, sign=1.0, occlude_zero=True, valid_mode=VALID_NONE):
-    """S driven by a flow field (N,2,H,W).  Returns (out, density, warped_mask, valid)."""
+def splat_flow(flow, data, data_mask=None, flow_mask=None, sign=1.0, occlude_zero=True, valid_mode=VALID_NONE,
+               want_aux=False):
+    """S driven by a flow field (N,2,H,W).  Returns (out, density, warped_mask, valid); density and warped_mask are
+    empty tensors unless `want_aux` (or autograd needs them)."""
     if data is None:
         f = flow.detach()
         out, density, wmask, _u, valid = _ops.splat_s_fwd(f[:, 0], f[:, 1], True, float(sign), None, data_mask,
-                                                          flow_mask, bool(occlude_zero), int(valid_mode))
+                                                          flow_mask, bool(occlude_zero), int(valid_mode), bool(want_aux))
+        return out, density, wmask, valid
+    if not want_aux and not (torch.is_grad_enabled() and (flow.requires_grad or data.requires_grad)):
+        f = flow.detach()
+        out, density, wmask, _u, valid = _ops.splat_s_fwd(f[:, 0], f[:, 1], True, float(sign), data.detach(), data_mask,
+                                                          flow_mask, bool(occlude_zero), int(valid_mode), False)
         return out, density, wmask, valid
     return _SplatFlow.apply(flow, data, data_mask, flow_mask, float(sign), bool(occlude_zero), int(valid_mode))
 
@@ -319,7 +332,7 @@ class _SplatFlow(torch.autograd.Function):
     def forward(ctx, flow, data, data_mask, flow_mask, sign, occlude_zero, valid_mode):
         flow = _f32c(flow)
         out, density, wmask, unocc, valid = _ops.splat_s_fwd(flow[:, 0], flow[:, 1], True, sign, data, data_mask,
-                                                             flow_mask, occlude_zero, valid_mode)
+                                                             flow_mask, occlude_zero, valid_mode, True)
         ctx.save_for_backward(flow, data, flow_mask, out, density, unocc)
         ctx.sign, ctx.occlude_zero = sign, occlude_zero
         ctx.mark_non_differentiable(wmask, valid)

@@ -10,6 +10,8 @@
 // channel is 0.  "mask channel == 1"  <=>  bad == 0 (and density >= 1e-3); both tests, and
 // density > 0, are sums of non-negative terms compared against zero and therefore independent of the
 // accumulation order (probe C9).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ofb {
@@ -149,6 +151,243 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const SplatParams 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v1 forward: interleaved accumulators, vector REDs, register merging, L2-resident per-item passes
+// ------------------------------------------------------------------------------------------------
+// The accumulator is this library's private workspace, so its layout is free: KP = 4 or 8 floats PER TARGET PIXEL
+// ([num_0 .. num_{C-1}, den, bad, pad]) instead of C+2 planes.  Every tap site is then ONE
+// red.global.add.v4.f32 (SASS REDG.E.ADD.F32x4) instead of C+2 scalar REDs, and the normalise pass reads one
+// float4 per pixel.  Contributions are merged in registers before they reach the L2 exactly as in the W adjoint
+// (csrc/warp_t.cu): lane l's east taps are lane l+1's west taps when the endpoints chain, and a thread carries its
+// south taps into the next source row.  Items are processed one (or a few) at a time -- zero-fill, accumulate,
+// normalise back to back on one small workspace -- so the accumulator lives in the 126 MB L2 and never reaches HBM.
+constexpr int kSplatRows = 8;      // source rows per thread; CTA tile = 64 x 32 (2 warps across x, 4 across y)
+
+template <int KP> struct AccVec { float v[KP]; };
+
+template <int KP>
+__device__ __forceinline__ void red_vec(float *acc, int q, const AccVec<KP> &a, bool pred)
+{
+    float *t = acc + (int64_t)q * KP;
+    if constexpr (KP == 1) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q red.global.add.f32 [%0], %1;\n\t}"
+                     ::"l"(t), "f"(a.v[0]), "r"((int)pred));
+    } else if constexpr (KP == 2) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q red.global.add.v2.f32 [%0], {%1, %2};\n\t}"
+                     ::"l"(t), "f"(a.v[0]), "f"(a.v[1]), "r"((int)pred));
+    } else {
+#pragma unroll
+        for (int h = 0; h < KP / 4; ++h)
+            asm volatile(
+                "{\n\t"
+                ".reg .pred q;\n\t"
+                "setp.ne.s32 q, %5, 0;\n\t"
+                "@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t"
+                "}" ::"l"(t + 4 * h), "f"(a.v[4 * h]), "f"(a.v[4 * h + 1]), "f"(a.v[4 * h + 2]), "f"(a.v[4 * h + 3]),
+                "r"((int)pred));
+    }
+}
+
+template <int C, bool HAS_BAD, int KP>
+__global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const SplatParams p, const int n0)
+{
+    static_assert(C + 1 + (HAS_BAD ? 1 : 0) <= KP, "accumulator slots");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * (4 * kSplatRows) + (warp >> 1) * kSplatRows;
+    const int n = n0 + blockIdx.z;
+    const int HW = p.H * p.W;
+    const bool active = x < p.W;                         // inactive lanes still take part in the shuffles
+    const int xc = min(x, p.W - 1);
+    const int rows = min(kSplatRows, p.H - y0);          // warp-uniform
+
+    const float *cx = p.cx + (int64_t)n * p.coord_bs, *cy = p.cy + (int64_t)n * p.coord_bs;
+    const float *data = (C > 0) ? p.data + (int64_t)n * p.data_bs : nullptr;
+    const uint8_t *dmask = HAS_BAD ? p.data_mask + (int64_t)n * p.data_mask_bs : nullptr;
+    const uint8_t *fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
+    float *acc = p.acc + (int64_t)blockIdx.z * HW * KP;  // workspace item = position inside the chunk
+    asm volatile("" : "+l"(cx), "+l"(cy), "+l"(data), "+l"(dmask), "+l"(fmask), "+l"(acc));
+
+    AccVec<KP> carry;                                    // south-tap sums waiting for the next source row
+#pragma unroll
+    for (int j = 0; j < KP; ++j) carry.v[j] = 0.0f;
+    int carry_o = 0;
+    bool carry_ok = false;
+
+    // software pipeline: the loads of source row r+1 are issued before row r is processed (the kernel is bound by
+    // memory latency at 3 CTAs/SM, and the volatile REDs below would otherwise pin the next row's loads behind them)
+    struct RowIn { float fx, fy, d[C > 0 ? C : 1]; uint8_t dm, fmk; };
+    auto load_row = [&](int r) {
+        RowIn in;
+        const int pix = (y0 + r) * p.W + xc;
+        in.fx = __ldg(cx + pix);
+        in.fy = __ldg(cy + pix);
+#pragma unroll
+        for (int c = 0; c < C; ++c) in.d[c] = __ldg(data + (c * HW + pix));
+        in.dm = HAS_BAD ? __ldg(dmask + pix) : 1;
+        in.fmk = fmask ? __ldg(fmask + pix) : 1;
+        return in;
+    };
+    RowIn nxt = load_row(0);
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+        const RowIn cur = nxt;
+        if (r + 1 < rows) nxt = load_row(r + 1);
+        const int y = y0 + r;
+        const float fx = cur.fx, fy = cur.fy;
+        float X = fx, Y = fy;
+        bool fm = active;
+        if (p.relative) {
+            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)x);                  // utils.py:1056-1057
+            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)y);
+            if (p.occlude_zero) fm = fm && !is_zero_vec(fx, fy);             // utils.py:1191-1192
+        }
+        fm = fm && (cur.fmk != 0);
+        // utils.py:1098-1111: floor, neighbours, weights times the in-bounds test (saturating conversion: far away
+        // and NaN positions fail the range tests / the w > 0 test below)
+        const float x0f = floorf(X), y0f = floorf(Y);
+        const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
+        const bool bx0 = (unsigned)xi < (unsigned)p.W, bx1 = (unsigned)(xi + 1) < (unsigned)p.W;
+        const bool by0 = (unsigned)yi < (unsigned)p.H, by1 = (unsigned)(yi + 1) < (unsigned)p.H;
+        const float ax0 = __fsub_rn(__fadd_rn(x0f, 1.0f), X), ax1 = __fsub_rn(X, x0f);
+        const float ay0 = __fsub_rn(__fadd_rn(y0f, 1.0f), Y), ay1 = __fsub_rn(Y, y0f);
+        const float w_nw = (fm && bx0 && by0) ? __fmul_rn(ay0, ax0) : 0.0f;   // utils.py:1114, 1123
+        const float w_ne = (fm && bx1 && by0) ? __fmul_rn(ay0, ax1) : 0.0f;
+        const float w_sw = (fm && bx0 && by1) ? __fmul_rn(ay1, ax0) : 0.0f;
+        const float w_se = (fm && bx1 && by1) ? __fmul_rn(ay1, ax1) : 0.0f;
+        const bool p_nw = w_nw > 0.0f, p_ne = w_ne > 0.0f, p_sw = w_sw > 0.0f, p_se = w_se > 0.0f;   // adding +0 is a no-op
+        const int o = (int)((unsigned)yi * (unsigned)p.W + (unsigned)xi);
+
+        const float *d = cur.d;
+        const float badf = (HAS_BAD && cur.dm == 0) ? 1.0f : 0.0f;
+
+        // per-tap accumulator vectors: [w*d_0 .. w*d_{C-1}, w, w*bad]   (utils.py:1133, 1139-1140)
+        AccVec<KP> top, bot, ene, ese;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            const float m = (j < C) ? d[j < C ? j : 0] : (j == C ? 1.0f : ((HAS_BAD && j == C + 1) ? badf : 0.0f));
+            top.v[j] = __fmul_rn(w_nw, m); ene.v[j] = __fmul_rn(w_ne, m);
+            bot.v[j] = __fmul_rn(w_sw, m); ese.v[j] = __fmul_rn(w_se, m);
+        }
+
+        // ---- horizontal merge with lane-1
+        const int prev_o = __shfl_up_sync(0xffffffffu, o, 1);
+        const unsigned pe = (p_ne ? 1u : 0u) | (p_se ? 2u : 0u);
+        const unsigned prev_pe = __shfl_up_sync(0xffffffffu, pe, 1);
+        const bool chain = (lane > 0) && (prev_o + 1 == o);
+        const bool merge_n = chain && (prev_pe & 1u) && p_nw;
+        const bool merge_s = chain && (prev_pe & 2u) && p_sw;
+        const unsigned bn = __ballot_sync(0xffffffffu, merge_n), bs = __ballot_sync(0xffffffffu, merge_s);
+        const bool taken_n = (lane < 31) && ((bn >> (lane + 1)) & 1u);
+        const bool taken_s = (lane < 31) && ((bs >> (lane + 1)) & 1u);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            if (j >= C + 1 + (HAS_BAD ? 1 : 0)) continue;                  // padding slots stay zero
+            const float pn = __shfl_up_sync(0xffffffffu, ene.v[j], 1), ps = __shfl_up_sync(0xffffffffu, ese.v[j], 1);
+            if (merge_n) top.v[j] += pn;
+            if (merge_s) bot.v[j] += ps;
+        }
+        // ---- vertical merge with the carried south taps of the previous source row
+        const bool vmerge = carry_ok && p_nw && (carry_o == o);
+        red_vec<KP>(acc, carry_o, carry, carry_ok && !vmerge);
+        if (vmerge) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) top.v[j] += carry.v[j];
+        }
+        red_vec<KP>(acc, o, top, p_nw);
+        red_vec<KP>(acc, o + 1, ene, p_ne && !taken_n);
+        red_vec<KP>(acc, o + p.W + 1, ese, p_se && !taken_s);
+        carry = bot;
+        carry_o = o + p.W;
+        carry_ok = p_sw;
+    }
+    red_vec<KP>(acc, carry_o, carry, carry_ok);
+}
+
+// normalise + masks + un-occlude fill from the interleaved accumulator (same arithmetic as splat_normalise_kernel)
+template <int C, bool HAS_BAD, int KP>
+__global__ void __launch_bounds__(256) splat_normalise_v1_kernel(const SplatParams p, const int n0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int n = n0 + blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const int HW = p.H * p.W;
+    const int pix = y * p.W + x;
+    const float *ab = p.acc + ((int64_t)blockIdx.z * HW + pix) * KP;
+    float a[KP];
+    if constexpr (KP == 1) {
+        a[0] = __ldcg(ab);
+    } else if constexpr (KP == 2) {
+        const float2 q = __ldcg(reinterpret_cast<const float2 *>(ab));
+        a[0] = q.x; a[1] = q.y;
+    } else {
+#pragma unroll
+        for (int h = 0; h < KP / 4; ++h) {
+            const float4 q = __ldcg(reinterpret_cast<const float4 *>(ab) + h);
+            a[4 * h] = q.x; a[4 * h + 1] = q.y; a[4 * h + 2] = q.z; a[4 * h + 3] = q.w;
+        }
+    }
+    const float den = a[C];
+    const float bad = HAS_BAD ? a[C + 1] : 0.0f;
+    const float dc = fmaxf(den, OFB_MIN_DENSITY);
+    const bool wm = den > 0.0f;
+    bool unocc = false;
+    if (p.occlude_zero && p.relative && !wm) {
+        const float fx = __ldg(p.cx + (int64_t)n * p.coord_bs + pix);
+        const float fy = __ldg(p.cy + (int64_t)n * p.coord_bs + pix);
+        unocc = is_zero_vec(fx, fy);
+        if (p.flow_mask) unocc = unocc && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix) != 0);
+    }
+    if (C > 0) {
+        const float *data = p.data + (int64_t)n * p.data_bs + pix;
+        float *out = p.out + (int64_t)n * C * HW + pix;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+            out[c * HW] = unocc ? __ldg(data + c * HW) : __fdiv_rn(a[c], dc);
+    }
+    if (p.density) p.density[(int64_t)n * HW + pix] = den;
+    if (p.warped_mask) p.warped_mask[(int64_t)n * HW + pix] = wm ? 1 : 0;
+    if (p.unocc) p.unocc[(int64_t)n * HW + pix] = unocc ? 1 : 0;
+    if (p.valid) {
+        float mch;
+        if (unocc) {
+            mch = (HAS_BAD && __ldg(p.data_mask + (int64_t)n * p.data_mask_bs + pix) == 0) ? 0.0f : 1.0f;
+        } else {
+            const float mnum = (bad == 0.0f) ? den : __fsub_rn(den, bad);
+            mch = __fdiv_rn(mnum, dc);
+        }
+        const bool ok = (p.valid_mode == OFB_VALID_EQ1) ? (mch == 1.0f) : (mch > 0.99999f);
+        p.valid[(int64_t)n * HW + pix] = ok ? 1 : 0;
+    }
+}
+
+typedef void (*SplatKernel)(const SplatParams, const int);
+struct SplatV1 { SplatKernel acc, norm; int kp; };
+
+template <int C>
+static SplatV1 splat_v1_for(bool bad)
+{
+    constexpr int KPb = (C + 2 <= 2) ? 2 : ((C + 2 <= 4) ? 4 : 8);
+    constexpr int KPn = (C + 1 <= 1) ? 1 : ((C + 1 <= 2) ? 2 : ((C + 1 <= 4) ? 4 : 8));
+    if (bad) return {splat_accumulate_v1_kernel<C, true, KPb>, splat_normalise_v1_kernel<C, true, KPb>, KPb};
+    return {splat_accumulate_v1_kernel<C, false, KPn>, splat_normalise_v1_kernel<C, false, KPn>, KPn};
+}
+
+static bool splat_v1(int C, bool bad, SplatV1 *k)
+{
+    switch (C) {
+        case 0: *k = splat_v1_for<0>(bad); return true;
+        case 1: *k = splat_v1_for<1>(bad); return true;
+        case 2: *k = splat_v1_for<2>(bad); return true;
+        case 3: *k = splat_v1_for<3>(bad); return true;
+        case 4: *k = splat_v1_for<4>(bad); return true;
+        case 5: *k = splat_v1_for<5>(bad); return true;
+        case 6: *k = splat_v1_for<6>(bad); return true;
+        default: return false;                          // wider payloads take the planar kernels
+    }
+}
+
 struct SplatBwdParams {
     const float *cx, *cy; int64_t coord_bs; int relative; float sign;
     const float *data; int64_t data_bs;
@@ -270,15 +509,199 @@ __global__ void __launch_bounds__(256) splat_bwd_kernel(const SplatBwdParams p, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// v1 adjoint: per-target prepass + vector tap gathers
+// ------------------------------------------------------------------------------------------------
+// The v0 gather evaluates gnum_c = g'_c/dc and gden at every tap: 2C+3 scalar gathers per tap, 4 taps per source.
+// Here a prepass writes G[p] = {gnum_0 .. gnum_{C-1}, gden} once per TARGET pixel, interleaved (KG = 2/4/8 floats),
+// and the per-source kernel fetches each tap with one 64/128-bit load.  
+template <int C, int KG>
+__global__ void __launch_bounds__(256) splat_bwd_prepass_kernel(const SplatBwdParams p, float *__restrict__ G)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int n = blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const int HW = p.H * p.W;
+    const int pix = y * p.W + x;
+    const float dq = __ldg(p.density + (int64_t)n * HW + pix);
+    const float dc = fmaxf(dq, OFB_MIN_DENSITY);
+    const bool dead = p.unocc && (__ldg(p.unocc + (int64_t)n * HW + pix) != 0);     // utils.py:1203 overwrote it
+    float v[KG];
+#pragma unroll
+    for (int j = 0; j < KG; ++j) v[j] = 0.0f;
+    float s = 0.0f;
+    if (!dead) {
+        const float *go = p.gout + (int64_t)n * C * HW + pix, *ou = p.out + (int64_t)n * C * HW + pix;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float g = __ldg(go + c * HW);
+            v[c] = g / dc;
+            s += g * __ldg(ou + c * HW);
+        }
+    }
+    float gden = p.gdensity ? __ldg(p.gdensity + (int64_t)n * HW + pix) : 0.0f;
+    if (!dead && dq >= OFB_MIN_DENSITY) gden -= s / dc;            // clamp_min passes the gradient where den >= 1e-3
+    v[C] = gden;
+    float *gp = G + ((int64_t)n * HW + pix) * KG;
+    if constexpr (KG == 2) {
+        *reinterpret_cast<float2 *>(gp) = make_float2(v[0], v[1]);
+    } else {
+#pragma unroll
+        for (int h = 0; h < KG / 4; ++h)
+            reinterpret_cast<float4 *>(gp)[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+    }
+}
+
+template <int KG>
+__device__ __forceinline__ void load_g(const float *__restrict__ G, int q, float (&v)[KG])
+{
+    const float *gp = G + (int64_t)q * KG;
+    if constexpr (KG == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(gp));
+        v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int h = 0; h < KG / 4; ++h) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(gp) + h);
+            v[4 * h] = t.x; v[4 * h + 1] = t.y; v[4 * h + 2] = t.z; v[4 * h + 3] = t.w;
+        }
+    }
+}
+
+template <int C, int KG>
+__global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdParams p, const float *__restrict__ G)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int n = blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const int HW = p.H * p.W;
+    const int pix = y * p.W + x;
+    const float fx = __ldg(p.cx + (int64_t)n * p.coord_bs + pix);
+    const float fy = __ldg(p.cy + (int64_t)n * p.coord_bs + pix);
+    float X = fx, Y = fy;
+    bool fm = true;
+    if (p.relative) {
+        X = __fadd_rn(__fmul_rn(p.sign, fx), (float)x);
+        Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)y);
+        if (p.occlude_zero) fm = !is_zero_vec(fx, fy);
+    }
+    if (p.flow_mask) fm = fm && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix) != 0);
+
+    float gd[C], gx = 0.0f, gy = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) gd[c] = 0.0f;
+    if (fm) {
+        const float *data = p.data + (int64_t)n * p.data_bs + pix;
+        float dat[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) dat[c] = __ldg(data + c * HW);
+        const float x0f = floorf(X), y0f = floorf(Y);
+        const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
+        const bool bx[2] = {(unsigned)xi < (unsigned)p.W, (unsigned)(xi + 1) < (unsigned)p.W};
+        const bool by[2] = {(unsigned)yi < (unsigned)p.H, (unsigned)(yi + 1) < (unsigned)p.H};
+        const float ax[2] = {__fsub_rn(__fadd_rn(x0f, 1.0f), X), __fsub_rn(X, x0f)};
+        const float ay[2] = {__fsub_rn(__fadd_rn(y0f, 1.0f), Y), __fsub_rn(Y, y0f)};
+        const float wx[2] = {bx[0] ? ax[0] : 0.0f, bx[1] ? ax[1] : 0.0f};      // utils.py:1110
+        const float wy[2] = {by[0] ? ay[0] : 0.0f, by[1] ? ay[1] : 0.0f};      // utils.py:1111
+        const float *Gn = G + (int64_t)n * HW * KG;
+        const int o = yi * p.W + xi;
+        float Gv[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                Gv[a][b] = 0.0f;
+                if (!(bx[b] && by[a])) continue;                            // contributes to nothing
+                float g[KG];
+                load_g<KG>(Gn, o + a * p.W + b, g);
+                const float w = __fmul_rn(wy[a], wx[b]);
+                float acc = g[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    acc = __fmaf_rn(g[c], dat[c], acc);
+                    gd[c] = __fmaf_rn(w, g[c], gd[c]);
+                }
+                Gv[a][b] = acc;
+            }
+        const float ibx0 = bx[0] ? 1.0f : 0.0f, ibx1 = bx[1] ? 1.0f : 0.0f;
+        const float iby0 = by[0] ? 1.0f : 0.0f, iby1 = by[1] ? 1.0f : 0.0f;
+        // d w / d x: wx[0] = (x1 - x)*inbx[0] -> -inbx[0];  wx[1] = (x - x0)*inbx[1] -> +inbx[1]
+        gx = wy[0] * (ibx1 * Gv[0][1] - ibx0 * Gv[0][0]) + wy[1] * (ibx1 * Gv[1][1] - ibx0 * Gv[1][0]);
+        gy = wx[0] * (iby1 * Gv[1][0] - iby0 * Gv[0][0]) + wx[1] * (iby1 * Gv[1][1] - iby0 * Gv[0][1]);
+        if (p.relative) {
+            gx *= p.sign;
+            gy *= p.sign;
+        }
+    }
+    if (p.gdata) {
+        const bool self_unocc = p.unocc && (__ldg(p.unocc + (int64_t)n * HW + pix) != 0);
+        float *gdp = p.gdata + (int64_t)n * C * HW + pix;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float v = gd[c];
+            if (self_unocc) v += __ldg(p.gout + ((int64_t)n * C + c) * HW + pix);
+            gdp[c * HW] = v;
+        }
+    }
+    if (p.gcx) {
+        p.gcx[(int64_t)n * p.gcoord_bs + pix] = gx;
+        p.gcy[(int64_t)n * p.gcoord_bs + pix] = gy;
+    }
+}
+
+typedef void (*SplatBwdPre)(const SplatBwdParams, float *);
+typedef void (*SplatBwdGat)(const SplatBwdParams, const float *);
+struct SplatBwdV1 { SplatBwdPre pre; SplatBwdGat gat; int kg; };
+
+template <int C>
+static SplatBwdV1 splat_bwd_v1_for()
+{
+    constexpr int KG = (C + 1 <= 2) ? 2 : ((C + 1 <= 4) ? 4 : 8);
+    return {splat_bwd_prepass_kernel<C, KG>, splat_bwd_gather_kernel<C, KG>, KG};
+}
+
+static bool splat_bwd_v1(int C, SplatBwdV1 *k)
+{
+    switch (C) {
+        case 1: *k = splat_bwd_v1_for<1>(); return true;
+        case 2: *k = splat_bwd_v1_for<2>(); return true;
+        case 3: *k = splat_bwd_v1_for<3>(); return true;
+        case 4: *k = splat_bwd_v1_for<4>(); return true;
+        case 5: *k = splat_bwd_v1_for<5>(); return true;
+        case 6: *k = splat_bwd_v1_for<6>(); return true;
+        case 7: *k = splat_bwd_v1_for<7>(); return true;
+        default: return false;
+    }
+}
+
 }  // namespace ofb
 
 using namespace ofb;
+
+// floats of workspace ofb_splat_s_fwd wants for this problem: one L2-sized chunk of interleaved accumulators for
+// the vector-RED path (C <= 6), C+2 planes per item for the planar path
+extern "C" int64_t ofb_splat_s_workspace(int N, int C, int H, int W, int has_data_mask)
+{
+    SplatV1 k;
+    if (N <= 0 || C < 0 || H <= 0 || W <= 0) return 0;
+    if (getenv("OFB_SPLAT_PLANAR") == nullptr && splat_v1(C, has_data_mask != 0, &k)) {
+        const int64_t item_floats = (int64_t)H * W * k.kp;
+        const long chunk_mb = getenv("OFB_SPLAT_CHUNK_MB") ? atol(getenv("OFB_SPLAT_CHUNK_MB")) : 1024;
+        int64_t chunk = ((int64_t)chunk_mb << 20) / (item_floats * 4);
+        if (chunk < 1) chunk = 1;
+        if (chunk > N) chunk = N;
+        return chunk * item_floats;
+    }
+    return (int64_t)N * (C + 2) * H * W;
+}
 
 extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
                                const float *data, int64_t data_bs,
                                const uint8_t *data_mask, int64_t data_mask_bs,
                                const uint8_t *flow_mask, int64_t flow_mask_bs,
-                               int occlude_zero, float *acc,
+                               int occlude_zero, float *acc, int64_t acc_floats,
                                float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
                                uint8_t *valid, int valid_mode,
                                int N, int C, int H, int W, void *stream)
@@ -289,11 +712,39 @@ extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_b
     if (H < 1 || W < 1) return OFB_ESHAPE;
     if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)N * (C + 2) * H * W, st);
-    if (e != cudaSuccess) return (int)e;
     SplatParams p{cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs,
                   flow_mask, flow_mask_bs, occlude_zero, acc, out, density, warped_mask, unocc,
                   valid, valid_mode, N, C, H, W};
+    SplatV1 k;
+    static const bool planar_only = getenv("OFB_SPLAT_PLANAR") != nullptr;
+    if (!planar_only && splat_v1(C, data_mask != nullptr, &k)) {
+        // chunk = as many items as keep the interleaved accumulator within ~48 MB (L2-resident), at least one; the
+        // workspace the caller provides (N*(C+2)*H*W floats) bounds it from above
+        const int64_t item_floats = (int64_t)H * W * k.kp;
+        static const long chunk_mb = getenv("OFB_SPLAT_CHUNK_MB") ? atol(getenv("OFB_SPLAT_CHUNK_MB")) : 1024;
+        int64_t chunk = ((int64_t)chunk_mb << 20) / (item_floats * 4);
+        const int64_t fit = acc_floats / item_floats;
+        if (chunk > fit) chunk = fit;
+        if (chunk < 1) chunk = 1;
+        if (chunk > N) chunk = N;
+        if (fit >= 1) {
+            const dim3 agrid((W + 63) / 64, (H + 4 * kSplatRows - 1) / (4 * kSplatRows), 1);
+            const dim3 nblock(32, 8);
+            for (int n0 = 0; n0 < N; n0 += (int)chunk) {
+                const int nn = (N - n0 < chunk) ? (N - n0) : (int)chunk;
+                cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)item_floats * nn, st);
+                if (e != cudaSuccess) return (int)e;
+                k.acc<<<dim3(agrid.x, agrid.y, nn), 256, 0, st>>>(p, n0);
+                OFB_CHECK_LAUNCH();
+                k.norm<<<dim3((W + 31) / 32, (H + 7) / 8, nn), nblock, 0, st>>>(p, n0);
+                OFB_CHECK_LAUNCH();
+            }
+            return 0;
+        }
+    }
+    if (acc_floats < (int64_t)N * (C + 2) * H * W) return OFB_EINVAL;     // planar path needs C+2 planes per item
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)N * (C + 2) * H * W, st);
+    if (e != cudaSuccess) return (int)e;
     const dim3 block(32, 8);
     const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
     splat_accumulate_kernel<<<grid, block, 0, st>>>(p);
@@ -303,12 +754,21 @@ extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_b
     return 0;
 }
 
+// floats of workspace ofb_splat_s_bwd wants (0: none, the generic gather is used)
+extern "C" int64_t ofb_splat_s_bwd_workspace(int N, int C, int H, int W)
+{
+    SplatBwdV1 k;
+    if (N <= 0 || H <= 0 || W <= 0 || !splat_bwd_v1(C, &k)) return 0;
+    return (int64_t)N * H * W * k.kg;
+}
+
 extern "C" int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
                                const float *data, int64_t data_bs,
                                const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
                                const float *out, const float *density, const uint8_t *unocc,
                                const float *gout, const float *gdensity,
                                float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                               float *work, int64_t work_floats,
                                int N, int C, int H, int W, void *stream)
 {
     if (!cx || !cy || !density || N <= 0 || C < 0) return OFB_EINVAL;
@@ -322,6 +782,14 @@ extern "C" int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_b
                      out, density, unocc, gout, gdensity, gcx, gcy, gcoord_bs, gdata, N, C, H, W};
     const dim3 block(32, 8);
     const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
+    SplatBwdV1 k;
+    if (work && splat_bwd_v1(C, &k) && work_floats >= (int64_t)N * H * W * k.kg) {
+        k.pre<<<grid, block, 0, st>>>(p, work);
+        OFB_CHECK_LAUNCH();
+        k.gat<<<grid, block, 0, st>>>(p, work);
+        OFB_CHECK_LAUNCH();
+        return 0;
+    }
     int c0 = 0;
     do {
         const int cn = (C - c0 < kMaxC) ? (C - c0) : kMaxC;

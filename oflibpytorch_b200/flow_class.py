@@ -316,6 +316,8 @@ class Flow(object):
                                      self._mask if (need_valid and flow_mask_and) else None,
                                      sign=sign, thresh=0.99999, want_valid=need_valid)
         else:
+            if consider_mask and payload_mask is self._mask:
+                payload_mask = None      # every source that is used has mask channel 1: the "bad weight" plane is zero
             out, _d, _w, valid = _ops.splat_flow(self._vecs, payload, payload_mask,
                                                  self._mask if consider_mask else None, sign=sign,
                                                  occlude_zero=True, valid_mode=VALID_GT if need_valid else VALID_NONE)
@@ -453,7 +455,8 @@ class Flow(object):
         """S(sign*v, [payload | m], m) with apply_flow's early-out (thresholded, unmasked; utils.py:497)."""
         if self._all_zero(thresholded=True, masked=False):
             return Flow._make(payload, out_ref, self._mask)
-        out, _d, _w, valid = _ops.splat_flow(self._vecs, payload, self._mask, self._mask, sign=sign,
+        # payload mask == flow mask here, so every contributing source has mask channel 1 (no "bad weight" plane)
+        out, _d, _w, valid = _ops.splat_flow(self._vecs, payload, None, self._mask, sign=sign,
                                              occlude_zero=True, valid_mode=VALID_GT)
         return Flow._make(out, out_ref, valid)
 
@@ -474,7 +477,8 @@ class Flow(object):
         if self._all_zero(thresholded=True, masked=False):           # apply_flow's early-out returns its input
             return self._mask.clone() if splat else self._mask.clone()
         if splat:
-            _o, _d, _w, valid = _ops.splat_flow(self._vecs, None, self._mask, self._mask if consider_mask else None,
+            _o, _d, _w, valid = _ops.splat_flow(self._vecs, None, None if consider_mask else self._mask,
+                                                self._mask if consider_mask else None,
                                                 sign=sign, occlude_zero=True, valid_mode=VALID_EQ1)
             return valid
         _o, valid = _ops.warp_t(self._vecs, None, None, self._mask, sign=sign, thresh=0.9999, want_valid=True)

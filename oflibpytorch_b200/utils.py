@@ -258,7 +258,7 @@ def apply_s_flow(flow: torch.Tensor, data: torch.Tensor, mask: torch.Tensor = No
     occlude_zero_flow = True if occlude_zero_flow is None else occlude_zero_flow
     _ops.require_cuda(flow, "flow")
     out, _density, wmask, _valid = _ops.splat_flow(flow, data.float(), None, mask, 1.0, bool(occlude_zero_flow),
-                                                   VALID_NONE)
+                                                   VALID_NONE, want_aux=True)
     return out, wmask
 
 
