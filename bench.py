@@ -163,6 +163,75 @@ def gpu_step(of, flow, img, mask, tmask, gout):
     return out, valid, gf, gi
 
 
+def secondary_workloads(of, dev, peak):
+    """BASELINE.json configs 3 and 4 through the public API, CUDA events, device-resident inputs.  Reported under
+    `other_workloads` for information; the bench line proper is config 2.  frac = algorithmic bytes
+    / time / measured HBM peak."""
+    def timeit(fn, steps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def entry(ms, px, bytes_per_px):
+        return {'ms': round(ms, 3), 'Mpix/s': round(px / ms / 1e3, 1),
+                'frac_of_hbm': round(bytes_per_px * px / (ms * 1e-3) / 1e9 / peak, 3), 'bytes_per_px': bytes_per_px}
+
+    res = {}
+    n = 32
+    flow = smooth_flow(n, H, W, 8.0, 5, dev)
+    flow[:, :, 200:440, 300:700] = 0.0
+    g = torch.Generator(device=dev).manual_seed(6)
+    img = torch.rand(n, C, H, W, generator=g, device=dev)
+    gout = torch.rand(n, C, H, W, generator=g, device=dev)
+    mask = torch.ones(n, H, W, dtype=torch.bool, device=dev)
+    mask[:, 300:500, 700:1100] = False
+    mask[:, :, ::97] = False
+    tmask = mask.roll(131, dims=2)
+    px = n * H * W
+
+    def s_fwd():
+        with torch.no_grad():
+            of.Flow(flow, 's', mask).apply(img, tmask, return_valid_area=True)
+
+    def s_fwdbwd():
+        f = flow.detach().requires_grad_()
+        i = img.detach().requires_grad_()
+        o, _v = of.Flow(f, 's', mask).apply(i, tmask, return_valid_area=True)
+        o.backward(gout)
+
+    res['cfg3 Flow.apply s + valid area, 32x3x1080x1920, fwd'] = entry(timeit(s_fwd), px, 35)
+    res['cfg3 Flow.apply s + valid area, 32x3x1080x1920, fwd+bwd'] = entry(timeit(s_fwdbwd), px, 35 + 69)
+    del flow, img, gout, mask, tmask
+    torch.cuda.empty_cache()
+    n, hh, ww = 16, 2160, 3840
+    fa, fb = smooth_flow(n, hh, ww, 8.0, 8, dev), smooth_flow(n, hh, ww, 8.0, 9, dev)
+    m = torch.ones(n, hh, ww, dtype=torch.bool, device=dev)
+    m[:, 600:1000, 1400:2200] = False
+    m[:, :, ::97] = False
+    px = n * hh * ww
+    for ref in 'ts':
+        a, b = of.Flow(fa, ref, m), of.Flow(fb, ref, m)
+
+        def comb():
+            with torch.no_grad():
+                return a.combine_with(b, 3)
+
+        def sw():
+            with torch.no_grad():
+                return a.switch_ref()
+
+        res['cfg4 combine_with mode 3 ref %s, 16x2160x3840, masked' % ref] = entry(timeit(comb), px, 27)
+        res['cfg4 switch_ref from %s, 16x2160x3840, masked' % ref] = entry(timeit(sw), px, 18)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -174,6 +243,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-chunk', type=int, default=8, help='batch items per pipelined chunk of the e2e path')
+    ap.add_argument('--extra', action='store_true', help='also time BASELINE.json configs 3 and 4 (information only)')
     ap.add_argument('--sigma', type=float, default=8.0, help='flow magnitude (px) of the synthetic field; 8 = the named config')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
@@ -305,6 +375,13 @@ def main():
                                    'H2D/compute/D2H on three streams' % args.e2e_chunk}
         del host_in, host_out
 
+    # ---------------------------------------------------------------- secondary workloads (information only)
+    extra = None
+    if rank == 0 and world == 1 and args.extra:
+        del flow, img, mask, tmask, gout
+        torch.cuda.empty_cache()
+        extra = secondary_workloads(of, dev, peak)
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -323,6 +400,7 @@ def main():
                        'l2': 'inputs (%.1f GB per step) exceed the 126 MB L2; no flush needed' % (
                            (BYTES_PER_PX['ofb_warp_t_fwd'] + BYTES_PER_PX['ofb_warp_t_bwd']) * px / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'other_workloads': extra,
         }
         print(json.dumps(line))
     if world > 1:

@@ -483,11 +483,25 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
 #pragma unroll
     for (int c = 0; c < CN; ++c) carry[c] = 0.0f;
 
+    // software pipeline: flow and upstream gradient of row r+1 are requested before row r is processed
+    struct RowIn { float fx, fy, g[CN]; };
+    auto load_row = [&](int r) {
+        RowIn in;
+        const int pix = (y0 + r) * p.W + xc;
+        in.fx = __ldg(fl + pix);
+        in.fy = __ldg(fl + (HW + pix));
+#pragma unroll
+        for (int c = 0; c < CN; ++c) in.g[c] = __ldg(go + (c * HW + pix));
+        return in;
+    };
+    RowIn nxt = load_row(0);
 #pragma unroll 2
     for (int r = 0; r < rows; ++r) {
+        const RowIn cur = nxt;
+        if (r + 1 < rows) nxt = load_row(r + 1);
         const int y = y0 + r;
         const int pix = y * p.W + xc;
-        const float fx = __ldg(fl + pix), fy = __ldg(fl + (HW + pix));
+        const float fx = cur.fx, fy = cur.fy;
         float ix, iy;
         sample_pos(cc, fx, fy, xf, (float)y, ix, iy);
         PixGeom g = pix_geom(ix, iy, p.W, p.H);
@@ -495,7 +509,7 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
 
         float gv[CN];
 #pragma unroll
-        for (int c = 0; c < CN; ++c) gv[c] = active ? __ldg(go + (c * HW + pix)) : 0.0f;
+        for (int c = 0; c < CN; ++c) gv[c] = active ? cur.g[c] : 0.0f;
 
         if (GFLOW) {
             float gix = 0.0f, giy = 0.0f;

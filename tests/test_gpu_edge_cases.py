@@ -1,0 +1,138 @@
+"""Edge cases of the CUDA path against the CPU oracle: smallest fields, wide payloads (planar fallback kernels),
+channel-group splits, non-contiguous / non-fp32 inputs, batch broadcasting, flows far outside the image."""
+import pytest
+import torch
+
+from helpers import assert_close, assert_grad_close, assert_mask_equal, gen, holed_mask, smooth_flow
+
+pytestmark = pytest.mark.gpu
+
+
+def of():
+    import oflibpytorch_b200
+    return oflibpytorch_b200
+
+
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def both(flow, ref, fmask, img, tmask, gout, consider_mask=True):
+    o = orc()
+    fo, io = flow.clone().requires_grad_(), img.clone().float().requires_grad_()
+    oo, vo = o.OFlow(fo, ref, fmask).apply(io, tmask, return_valid_area=True, consider_mask=consider_mask)
+    oo.backward(gout)
+    fg, ig = flow.cuda().requires_grad_(), img.cuda().float().requires_grad_()
+    og, vg = of().Flow(fg, ref, None if fmask is None else fmask.cuda()).apply(
+        ig, None if tmask is None else tmask.cuda(), return_valid_area=True, consider_mask=consider_mask)
+    og.backward(gout.cuda())
+    assert_close(og, oo, 'out')
+    assert_mask_equal(vg, vo, 'valid')
+    assert_grad_close(fg.grad, fo.grad, 'gflow')
+    assert_grad_close(ig.grad, io.grad, 'gimg')
+
+
+@pytest.mark.parametrize('ref', ['t', 's'])
+@pytest.mark.parametrize('shape', [(1, 1, 2, 2), (1, 2, 2, 7), (2, 1, 9, 2), (1, 3, 3, 3), (1, 1, 64, 65), (1, 2, 33, 128)])
+def test_tiny_and_odd_fields(ref, shape):
+    n, c, h, w = shape
+    flow = torch.randn(n, 2, h, w, generator=gen(900 + h * w)) * 1.5
+    both(flow, ref, holed_mask(n, h, w, 901), torch.rand(n, c, h, w, generator=gen(902)),
+         holed_mask(n, h, w, 903), torch.rand(n, c, h, w, generator=gen(904)))
+
+
+@pytest.mark.parametrize('ref', ['t', 's'])
+@pytest.mark.parametrize('c', [4, 5, 7, 8, 9, 13])
+def test_wide_payloads(ref, c):
+    """C > 4 splits into channel groups (W) / takes KP = 8 or the planar splat kernels (S)."""
+    n, h, w = 2, 40, 56
+    flow = smooth_flow(n, h, w, 3.0, 910 + c)
+    both(flow, ref, holed_mask(n, h, w, 911), torch.rand(n, c, h, w, generator=gen(912)),
+         holed_mask(n, h, w, 913), torch.rand(n, c, h, w, generator=gen(914)))
+    both(flow, ref, None, torch.rand(n, c, h, w, generator=gen(915)), None, torch.rand(n, c, h, w, generator=gen(916)))
+
+
+@pytest.mark.parametrize('ref', ['t', 's'])
+def test_flows_far_outside_the_image(ref):
+    n, c, h, w = 2, 2, 24, 40
+    flow = torch.randn(n, 2, h, w, generator=gen(920)) * 30
+    flow[0, :, :5] = 1e6                    # nothing of these rows lands anywhere
+    flow[1, :, 10:12] = -3e9
+    both(flow, ref, holed_mask(n, h, w, 921), torch.rand(n, c, h, w, generator=gen(922)), holed_mask(n, h, w, 923),
+         torch.rand(n, c, h, w, generator=gen(924)))
+
+
+@pytest.mark.parametrize('ref', ['t', 's'])
+def test_non_contiguous_and_other_dtypes(ref):
+    m, o = of(), orc()
+    n, c, h, w = 2, 3, 30, 44
+    flow_hwc = smooth_flow(n, h, w, 3.0, 930).permute(0, 2, 3, 1).contiguous()        # (N,H,W,2) layout
+    img64 = torch.rand(n, c, h, w, generator=gen(931), dtype=torch.float64)
+    img_nc = torch.rand(n, h, w, c, generator=gen(932)).permute(0, 3, 1, 2)            # non-contiguous view
+    fo = o.OFlow(flow_hwc.permute(0, 3, 1, 2).contiguous(), ref)
+    fg = m.Flow(flow_hwc.cuda(), ref)
+    assert fg.shape == (n, h, w)
+    r = fg.apply(img64.cuda())
+    assert r.dtype == torch.float64
+    assert_close(r, fo.apply(img64), 'float64 target')
+    assert_close(fg.apply(img_nc.cuda()), fo.apply(img_nc.contiguous()), 'non-contiguous target')
+    half = torch.rand(n, c, h, w, generator=gen(933)).half()
+    assert fg.apply(half.cuda()).dtype == torch.float16
+    i16 = (torch.rand(n, c, h, w, generator=gen(934)) * 1000).to(torch.int16)
+    assert torch.equal(m.apply_flow(fg.vecs, i16.cuda(), ref).cpu(), o.apply_flow(fo.vecs, i16, ref)) or \
+        float((m.apply_flow(fg.vecs, i16.cuda(), ref).cpu() - o.apply_flow(fo.vecs, i16, ref)).abs().max()) <= 1
+
+
+@pytest.mark.parametrize('ref', ['t', 's'])
+def test_batch_broadcasting_with_gradients(ref):
+    """one flow, many targets and many flows, one target: gradients of the broadcast operand are summed."""
+    m, o = of(), orc()
+    n, c, h, w = 3, 2, 26, 38
+    flow1, flown = smooth_flow(1, h, w, 3.0, 940), smooth_flow(n, h, w, 3.0, 941)
+    img1, imgn = torch.rand(1, c, h, w, generator=gen(942)), torch.rand(n, c, h, w, generator=gen(943))
+    gout = torch.rand(n, c, h, w, generator=gen(944))
+    for fl, im in ((flow1, imgn), (flown, img1)):
+        fo, io = fl.clone().requires_grad_(), im.clone().requires_grad_()
+        o.apply_flow(fo, io, ref).backward(gout)
+        fg, ig = fl.cuda().requires_grad_(), im.cuda().requires_grad_()
+        r = m.apply_flow(fg, ig, ref)
+        r.backward(gout.cuda())
+        assert r.shape == (n, c, h, w)
+        assert_close(r, o.apply_flow(fl, im, ref), 'out')
+        assert_grad_close(fg.grad, fo.grad, 'gflow')
+        assert_grad_close(ig.grad, io.grad, 'gimg')
+
+
+def test_grid_from_unstructured_density_gradient_and_validity_modes():
+    m, o = of(), orc()
+    n, c, h, w = 2, 2, 28, 36
+    x = (torch.rand(n, h, w, generator=gen(950)) * (w + 4) - 2)
+    y = (torch.rand(n, h, w, generator=gen(951)) * (h + 4) - 2)
+    d = torch.randn(n, c, h, w, generator=gen(952))
+    gd = torch.rand(n, h, w, generator=gen(953))
+    xo, yo, do = (t.clone().requires_grad_() for t in (x, y, d))
+    oo, deno = o.grid_from_unstructured_data(xo, yo, do)
+    (deno * gd).sum().backward()                                     # gradient ONLY through the density output
+    xg, yg, dg = (t.cuda().requires_grad_() for t in (x, y, d))
+    og, deng = m.grid_from_unstructured_data(xg, yg, dg)
+    (deng * gd.cuda()).sum().backward()
+    assert_close(og, oo, 'data')
+    assert_close(deng, deno, 'density')
+    assert_grad_close(xg.grad, xo.grad, 'gx')
+    assert_grad_close(yg.grad, yo.grad, 'gy')
+    assert float(dg.grad.abs().max()) == 0.0 and float(do.grad.abs().max()) == 0.0
+
+
+def test_apply_s_flow_returns_warped_mask_and_density_path():
+    m, o = of(), orc()
+    n, c, h, w = 2, 3, 31, 47
+    flow = smooth_flow(n, h, w, 4.0, 960)
+    flow[:, :, 8:14, 10:30] = 0.0
+    img, mask = torch.rand(n, c, h, w, generator=gen(961)), holed_mask(n, h, w, 962)
+    for occ in (True, False):
+        with torch.no_grad():
+            og, wg = m.apply_s_flow(flow.cuda(), img.cuda(), mask.cuda(), occ)
+        oo, wo = o.apply_s_flow(flow, img, mask, occ)
+        assert_close(og, oo, 'out')
+        assert_mask_equal(wg, wo, 'warped mask')
