@@ -141,6 +141,15 @@ int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_bs, int rela
  * generic scalar-gather kernel runs). */
 int64_t ofb_splat_s_bwd_workspace(int N, int C, int H, int W);
 
+/* Point sampling of a flow field -- the sparse half of track_pts (utils.py:1003-1019): out[n,m,:] = (flow_y, flow_x)
+ * bilinearly interpolated at pts[n,m,:] = (y, x) with grid_sample(align_corners=True, zeros) semantics.
+ *   flow (N|1, 2, H, W); pts, out (N, M, 2).  The adjoint yields gflow (N|1,2,H,W; zero-filled by the call; stride 0
+ *   accumulates over the batch) and gpts (N, M, 2); either may be NULL. */
+int ofb_sample_pts_fwd(const float *flow, int64_t flow_bs, const float *pts, float *out,
+                       int N, int M, int H, int W, void *stream);
+int ofb_sample_pts_bwd(const float *flow, int64_t flow_bs, const float *pts, const float *gout,
+                       float *gflow, int64_t gflow_bs, float *gpts, int N, int M, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,10 +8,10 @@ Drop-in for: ``apply_flow``, ``combine_flows`` (modes 1/2/3), ``switch_flow_ref`
 from .flow_class import Flow
 from .flow_operations import combine_flows, invert_flow, switch_flow_ref, valid_source, valid_target
 from .utils import (DEFAULT_THRESHOLD, apply_flow, apply_s_flow, get_flow_endpoints, get_pure_pytorch,
-                    grid_from_unstructured_data, is_zero_flow, set_pure_pytorch, threshold_vectors,
+                    grid_from_unstructured_data, is_zero_flow, set_pure_pytorch, threshold_vectors, track_pts,
                     unset_pure_pytorch)
 
 __version__ = '0.1.0'
 __all__ = ['Flow', 'combine_flows', 'invert_flow', 'switch_flow_ref', 'valid_source', 'valid_target',
            'apply_flow', 'apply_s_flow', 'get_flow_endpoints', 'grid_from_unstructured_data', 'is_zero_flow',
-           'threshold_vectors', 'get_pure_pytorch', 'set_pure_pytorch', 'unset_pure_pytorch', 'DEFAULT_THRESHOLD']
+           'threshold_vectors', 'track_pts', 'get_pure_pytorch', 'set_pure_pytorch', 'unset_pure_pytorch', 'DEFAULT_THRESHOLD']

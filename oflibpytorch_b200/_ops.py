@@ -354,6 +354,58 @@ class _SplatFlow(torch.autograd.Function):
         return gflow, gdata, None, None, None, None, None
 
 
+_lib.define("sample_pts_fwd(Tensor flow, Tensor pts) -> Tensor")
+_lib.define("sample_pts_bwd(Tensor flow, Tensor pts, Tensor gout, bool need_gflow, bool need_gpts) -> (Tensor, Tensor)")
+
+
+def _sample_pts_fwd(flow, pts):
+    require_cuda(flow, "flow")
+    flow, pts = _f32c(flow), _f32c(pts)
+    n, m, _ = pts.shape
+    _, _, h, w = flow.shape
+    with torch.cuda.device(flow.device):
+        out = torch.empty((n, m, 2), dtype=torch.float32, device=flow.device)
+        _call("ofb_sample_pts_fwd", _p(flow), _bs(flow, n, 2 * h * w), _p(pts), _p(out), n, m, h, w, _stream())
+    return out
+
+
+def _sample_pts_bwd(flow, pts, gout, need_gflow, need_gpts):
+    require_cuda(flow, "flow")
+    flow, pts, gout = _f32c(flow), _f32c(pts), _f32c(gout)
+    n, m, _ = pts.shape
+    _, _, h, w = flow.shape
+    with torch.cuda.device(flow.device):
+        gflow = torch.empty(tuple(flow.shape) if need_gflow else (0,), dtype=torch.float32, device=flow.device)
+        gpts = torch.empty((n, m, 2) if need_gpts else (0,), dtype=torch.float32, device=flow.device)
+        _call("ofb_sample_pts_bwd", _p(flow), _bs(flow, n, 2 * h * w), _p(pts), _p(gout),
+              _p(gflow) if need_gflow else None, _bs(flow, n, 2 * h * w), _p(gpts) if need_gpts else None,
+              n, m, h, w, _stream())
+    return gflow, gpts
+
+
+_lib.impl("sample_pts_fwd", _sample_pts_fwd, "CUDA")
+_lib.impl("sample_pts_bwd", _sample_pts_bwd, "CUDA")
+
+
+class _SamplePts(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, pts):
+        ctx.save_for_backward(flow, pts)
+        return _ops.sample_pts_fwd(flow, pts)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        flow, pts = ctx.saved_tensors
+        gf, gp = _ops.sample_pts_bwd(flow, pts, gout, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return (gf if ctx.needs_input_grad[0] else None), (gp if ctx.needs_input_grad[1] else None)
+
+
+def sample_pts(flow, pts):
+    """(N,M,2) flow vectors in (y, x) order interpolated at float points pts (N,M,2) in (y, x) order."""
+    return _SamplePts.apply(flow, pts)
+
+
 def splat_xy(x, y, data, mask=None):
     """S with absolute coordinates (grid_from_unstructured_data, utils.py:1061).  Returns (out, density)."""
     out, density, _w, _v = _SplatS.apply(x, y, data, None, mask, False, 1.0, False, VALID_NONE)

@@ -25,7 +25,7 @@ import torch.nn.functional as f
 from . import _ops
 from ._ops import VALID_EQ1, VALID_GT, VALID_NONE
 from .utils import (STAT_NONFINITE, _is_zero_from_stats, _restore_dtype, _valid_vecs, get_pure_pytorch,
-                    get_valid_device, get_valid_mask, get_valid_padding, get_valid_ref, get_valid_shape)
+                    get_valid_device, get_valid_mask, get_valid_padding, get_valid_ref, get_valid_shape, track_pts)
 
 FlowAlias = 'Flow'
 
@@ -435,6 +435,30 @@ class Flow(object):
         if return_valid_area:
             return warped, valid
         return warped
+
+    def track(self, pts: torch.Tensor, int_out: bool = None, get_valid_status: bool = None):
+        """Warp points with the flow (reference flow_class.py:961-1020).  With `get_valid_status` also returns, per
+        point, whether it is tracked by a valid vector and lands inside the field (= `valid_source` at the point)."""
+        input_2d = pts.dim() == 2
+        get_valid_status = False if get_valid_status is None else get_valid_status
+        if not isinstance(get_valid_status, bool):
+            raise TypeError("Error tracking points: Get_tracked needs to be a boolean")
+        warped_pts = track_pts(flow=self._vecs, ref=self._ref, pts=pts, int_out=int_out)
+        if input_2d and self.shape[0] == 1:
+            warped_pts = warped_pts.squeeze(0)
+        if not get_valid_status:
+            return warped_pts
+        if pts.dtype.is_floating_point:
+            pts = torch.round(pts)
+        pts2 = (pts.unsqueeze(0) if input_2d else pts).to(self._device)
+        if pts2.shape[0] != self.shape[0]:
+            pts2 = pts2.expand(self.shape[0], -1, -1)
+        valid_source = self.valid_source().view(self.shape[0], -1)
+        idx = (pts2[..., 0] * self.shape[-1] + pts2[..., 1]).long()
+        status = torch.gather(valid_source, 1, idx)
+        if warped_pts.dim() == 2:
+            status = status.squeeze(0)
+        return warped_pts, status
 
     # ------------------------------------------------------------------ ref switching and inversion
     def switch_ref(self, mode: str = None) -> FlowAlias:

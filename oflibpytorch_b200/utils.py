@@ -326,3 +326,52 @@ def apply_flow(flow: Union[np.ndarray, torch.Tensor], target: torch.Tensor, ref:
     else:
         result, _d, _w, _v = _ops.splat_flow(flow, t, None, mask, 1.0, True, VALID_NONE)   # utils.py:576
     return _restore_dtype(_restore_shape(result, target_dims), target_dtype)
+
+
+def track_pts(flow: Union[np.ndarray, torch.Tensor], ref: str, pts: torch.Tensor, int_out: bool = None) -> torch.Tensor:
+    """Warp points with a flow field (reference utils.py:941-1042, PURE_PYTORCH path).  Differentiable w.r.t. the flow
+    and float points.  `pts` is (M,2) or (N,M,2) in (y, x) order.  SURVEY.md section 8(f2)."""
+    flow, stats = _valid_vecs(flow, error_string="Error tracking points: ", want_stats=True)
+    ref = get_valid_ref(ref)
+    if not isinstance(pts, torch.Tensor):
+        raise TypeError("Error tracking points: Pts needs to be a numpy array or a torch tensor")
+    return_2d = False
+    if pts.dim() == 2:
+        return_2d = True
+        pts = pts.unsqueeze(0).expand(flow.shape[0], -1, -1)
+    elif pts.dim() == 3:
+        if pts.shape[0] != flow.shape[0]:
+            if pts.shape[0] == 1:
+                pts = pts.expand(flow.shape[0], -1, -1)
+            else:
+                raise ValueError("Error tracking points: "
+                                 "If used, pts batch size needs to be equal to the flow batch size")
+    else:
+        raise ValueError("Error tracking points: Pts needs to have shape M-2 or N-M-2")
+    if pts.shape[-1] != 2:
+        raise ValueError("Error tracking points: Pts needs to have shape M-2 or N-M-2")
+    int_out = False if int_out is None else int_out
+    if not isinstance(int_out, bool):
+        raise TypeError("Error tracking points: Int_out needs to be a boolean")
+    _ops.require_cuda(flow, "flow")
+    pts = pts.to(flow.device)
+
+    if all(_is_zero_from_stats(stats, True, False)):                           # utils.py:993
+        warped_pts = pts
+    else:
+        if ref == 't':
+            # utils.py:999-1001: bring the 't' flow to the source grid with one splat whose payload is the flow itself
+            flow, _d, _w, _v = _ops.splat_flow(flow, flow, None, None, -1.0, False, VALID_NONE)
+        if not pts.dtype.is_floating_point:                                    # utils.py:1003-1008
+            n, _, h, w = flow.shape
+            idx = (pts[..., 0] * w + pts[..., 1]).long().unsqueeze(-1).expand(-1, -1, 2)
+            flow_vecs = torch.gather(flow.permute(0, 2, 3, 1).reshape(n, h * w, 2), 1, idx).flip(-1)
+        else:                                                                  # utils.py:1010-1018
+            flow_vecs = _ops.sample_pts(flow, pts.to(torch.float))
+        warped_pts = pts.float() + flow_vecs
+        warped_pts = torch.where(torch.isnan(warped_pts).any(-1, keepdim=True), torch.zeros_like(warped_pts), warped_pts)
+    if int_out:
+        warped_pts = torch.round(warped_pts).long()
+    if return_2d:
+        warped_pts = warped_pts.squeeze(0)
+    return warped_pts

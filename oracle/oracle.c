@@ -375,3 +375,63 @@ void orc_is_zero_flow(const float *flow, int thresholded, uint8_t *out, int N, i
         out[n] = (uint8_t)all;
     }
 }
+
+/* ------------------------------------------------------------------------- */
+/* point sampling (track_pts, utils.py:1003-1019)                            */
+/* ------------------------------------------------------------------------- */
+
+/* out[n,m,:] = (flow_y, flow_x) interpolated at pts[n,m,:] = (y, x): grid_sample(flow, normalise_coords(pts flipped),
+ * align_corners=True) followed by .flip(1) (utils.py:1010-1018), with ATen's accumulation order. */
+void orc_sample_pts_fwd(const float *flow, const float *pts, float *out, int N, int M, int H, int W)
+{
+    const int64_t HW = (int64_t)H * W;
+    for (int n = 0; n < N; ++n)
+        for (int m = 0; m < M; ++m) {
+            const float *pp = pts + ((int64_t)n * M + m) * 2;
+            float ix = orc_round_trip(pp[1], (float)(W - 1)), iy = orc_round_trip(pp[0], (float)(H - 1));
+            float x0 = floorf(ix), y0 = floorf(iy), x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+            float nw = (x1 - ix) * (y1 - iy), ne = (ix - x0) * (y1 - iy), sw = (x1 - ix) * (iy - y0), se = (ix - x0) * (iy - y0);
+            int b_nw = orc_inb(x0, y0, H, W), b_ne = orc_inb(x1, y0, H, W), b_sw = orc_inb(x0, y1, H, W), b_se = orc_inb(x1, y1, H, W);
+            for (int c = 0; c < 2; ++c) {
+                const float *t = flow + ((int64_t)n * 2 + c) * HW;
+                float a = b_nw ? t[(int64_t)y0 * W + (int64_t)x0] : 0.0f, b = b_ne ? t[(int64_t)y0 * W + (int64_t)x1] : 0.0f;
+                float cc = b_sw ? t[(int64_t)y1 * W + (int64_t)x0] : 0.0f, d = b_se ? t[(int64_t)y1 * W + (int64_t)x1] : 0.0f;
+                float r = a * nw;
+                r = fmaf(b, ne, r);
+                r = fmaf(cc, sw, r);
+                r = fmaf(d, se, r);
+                out[((int64_t)n * M + m) * 2 + (1 - c)] = r;
+            }
+        }
+}
+
+/* adjoint: gflow (N,2,H,W) and gpts (N,M,2, (y,x) order) are overwritten */
+void orc_sample_pts_bwd(const float *flow, const float *pts, const float *gout, float *gflow, float *gpts,
+                        int N, int M, int H, int W)
+{
+    const int64_t HW = (int64_t)H * W;
+    memset(gflow, 0, sizeof(float) * (size_t)N * 2 * HW);
+    for (int n = 0; n < N; ++n)
+        for (int m = 0; m < M; ++m) {
+            const float *pp = pts + ((int64_t)n * M + m) * 2;
+            float ix = orc_round_trip(pp[1], (float)(W - 1)), iy = orc_round_trip(pp[0], (float)(H - 1));
+            float x0 = floorf(ix), y0 = floorf(iy), x1 = x0 + 1.0f, y1 = y0 + 1.0f;
+            float ex = x1 - ix, wx = ix - x0, sy = y1 - iy, ny = iy - y0;
+            int b_nw = orc_inb(x0, y0, H, W), b_ne = orc_inb(x1, y0, H, W), b_sw = orc_inb(x0, y1, H, W), b_se = orc_inb(x1, y1, H, W);
+            float gx = 0.0f, gy = 0.0f;
+            for (int c = 0; c < 2; ++c) {
+                float g = gout[((int64_t)n * M + m) * 2 + (1 - c)];
+                const float *t = flow + ((int64_t)n * 2 + c) * HW;
+                float *gt = gflow + ((int64_t)n * 2 + c) * HW;
+                float a = 0, b = 0, cc = 0, d = 0;
+                if (b_nw) { a = t[(int64_t)y0 * W + (int64_t)x0]; gt[(int64_t)y0 * W + (int64_t)x0] += ex * sy * g; }
+                if (b_ne) { b = t[(int64_t)y0 * W + (int64_t)x1]; gt[(int64_t)y0 * W + (int64_t)x1] += wx * sy * g; }
+                if (b_sw) { cc = t[(int64_t)y1 * W + (int64_t)x0]; gt[(int64_t)y1 * W + (int64_t)x0] += ex * ny * g; }
+                if (b_se) { d = t[(int64_t)y1 * W + (int64_t)x1]; gt[(int64_t)y1 * W + (int64_t)x1] += wx * ny * g; }
+                gx += g * ((b - a) * sy + (d - cc) * ny);
+                gy += g * ((cc - a) * ex + (d - b) * wx);
+            }
+            gpts[((int64_t)n * M + m) * 2] = gy;
+            gpts[((int64_t)n * M + m) * 2 + 1] = gx;
+        }
+}

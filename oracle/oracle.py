@@ -52,6 +52,9 @@ def lib():
         _lib.orc_flow_endpoints.argtypes = [_F, ctypes.c_float, _F, _F, _I, _I, _I]
         _lib.orc_zero_mask.argtypes = [_F, _F, _I, _I, _I]
         _lib.orc_is_zero_flow.argtypes = [_F, _I, _F, _I, _I, _I]
+        _lib.orc_sample_pts_fwd.argtypes = [_F, _F, _F, _I, _I, _I, _I]
+        _lib.orc_sample_pts_bwd.argtypes = [_F, _F, _F, _F, _F, _I, _I, _I, _I]
+        _lib.orc_sample_pts_fwd.restype = _lib.orc_sample_pts_bwd.restype = None
         for f in ("orc_warp_t_fwd", "orc_warp_t_bwd", "orc_grid_from_unstructured",
                   "orc_grid_from_unstructured_bwd", "orc_flow_endpoints", "orc_zero_mask",
                   "orc_is_zero_flow"):
@@ -395,6 +398,72 @@ class OFlow:
         if s:
             return self + self.invert(ref='t').apply(flow)
         return flow + flow.apply(self)
+
+
+class _SamplePts(torch.autograd.Function):
+    """flow vectors (y, x) interpolated at float points (utils.py:1010-1018)."""
+
+    @staticmethod
+    def forward(ctx, flow, pts):
+        f, p = _f32(flow), _f32(pts)
+        n, m, _ = p.shape
+        out = torch.empty((n, m, 2), dtype=torch.float32)
+        lib().orc_sample_pts_fwd(_p(f), _p(p), _p(out), n, m, f.shape[2], f.shape[3])
+        ctx.save_for_backward(f, p)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        f, p = ctx.saved_tensors
+        n, m, _ = p.shape
+        gf, gp = torch.empty_like(f), torch.empty_like(p)
+        lib().orc_sample_pts_bwd(_p(f), _p(p), _p(_f32(gout)), _p(gf), _p(gp), n, m, f.shape[2], f.shape[3])
+        return gf, gp
+
+
+def track_pts(flow, ref, pts, int_out=False):
+    """utils.py:941-1042, PURE_PYTORCH path; flow (N,2,H,W) tensor, pts (M,2) or (N,M,2) in (y, x) order."""
+    flow = flow.float()
+    return_2d = pts.dim() == 2
+    if return_2d:
+        pts = pts.unsqueeze(0).expand(flow.shape[0], -1, -1)
+    elif pts.shape[0] != flow.shape[0]:
+        pts = pts.expand(flow.shape[0], -1, -1)
+    if bool(is_zero_flow(flow, True).all()):
+        warped = pts
+    else:
+        if ref == 't':
+            x, y = get_flow_endpoints(-flow, 's')
+            flow, _ = grid_from_unstructured_data(x, y, flow)
+        if not pts.dtype.is_floating_point:
+            n, _, h, w = flow.shape
+            idx = (pts[..., 0] * w + pts[..., 1]).long().unsqueeze(-1).expand(-1, -1, 2)
+            vec = torch.gather(flow.permute(0, 2, 3, 1).reshape(n, h * w, 2), 1, idx).flip(-1)
+        else:
+            vec = _SamplePts.apply(flow, pts.float().contiguous())
+        warped = pts.float() + vec
+        warped = torch.where(torch.isnan(warped).any(-1, keepdim=True), torch.zeros_like(warped), warped)
+    if int_out:
+        warped = torch.round(warped).long()
+    return warped.squeeze(0) if return_2d else warped
+
+
+def flow_track(fl: "OFlow", pts, int_out=False, get_valid_status=False):
+    """flow_class.py:961-1020"""
+    input_2d = pts.dim() == 2
+    warped = track_pts(fl.vecs, fl.ref, pts, int_out)
+    if input_2d and fl.shape[0] == 1:
+        warped = warped.squeeze(0)
+    if not get_valid_status:
+        return warped
+    if pts.dtype.is_floating_point:
+        pts = torch.round(pts)
+    pts2 = pts.unsqueeze(0) if input_2d else pts
+    if pts2.shape[0] != fl.shape[0]:
+        pts2 = pts2.expand(fl.shape[0], -1, -1)
+    vs = fl.valid_source().view(fl.shape[0], -1)
+    status = torch.gather(vs, 1, (pts2[..., 0] * fl.shape[-1] + pts2[..., 1]).long())
+    return warped, (status.squeeze(0) if warped.dim() == 2 else status)
 
 
 def combine(a: OFlow, b: OFlow, mode: int, ref=None) -> OFlow:

@@ -71,5 +71,23 @@ for mode in (1, 2, 3):
                 k = 'cmbx_%d%s%s%s' % (mode, ra, rb, ro)
                 out[k + '_v'], out[k + '_m'] = r.vecs.numpy(), r.mask.numpy()
                 assert r.ref == ro
+# utils.py:941-1042 track_pts / flow_class.py:961-1020 Flow.track: float and integer points, both refs, status
+tf = smooth(3)
+tm = torch.rand(2, 30, 44, generator=g) > 0.1
+pf = torch.stack((torch.rand(2, 17, generator=g) * 29, torch.rand(2, 17, generator=g) * 43), -1)   # (N, M, (y, x))
+pi = torch.stack((torch.randint(0, 30, (2, 17), generator=g), torch.randint(0, 44, (2, 17), generator=g)), -1)
+gp = torch.rand(2, 17, 2, generator=g)
+out['trk_flow'], out['trk_mask'], out['trk_pf'], out['trk_pi'], out['trk_gp'] = tf.numpy(), tm.numpy(), pf.numpy(), pi.numpy(), gp.numpy()
+for ref in 'st':
+    f2 = tf.clone().requires_grad_()
+    p2 = pf.clone().requires_grad_()
+    w = of.track_pts(f2, ref, p2)
+    w.backward(gp)
+    out['trk_%s_f' % ref], out['trk_%s_f_gflow' % ref], out['trk_%s_f_gpts' % ref] = w.detach().numpy(), f2.grad.numpy(), p2.grad.numpy()
+    out['trk_%s_i' % ref] = of.track_pts(tf, ref, pi).numpy()
+    out['trk_%s_f_int' % ref] = of.track_pts(tf, ref, pf, int_out=True).numpy()
+    out['trk_%s_f_2d' % ref] = of.track_pts(tf, ref, pf[0]).numpy()
+    wp, st = of.Flow(tf, ref, tm).track(pf, get_valid_status=True)
+    out['trk_%s_flowtrack' % ref], out['trk_%s_status' % ref] = wp.numpy(), st.numpy()
 np.savez_compressed(os.path.join(HERE, 'kats_v1.npz'), **out)
 print('wrote', len(out), 'arrays', os.path.getsize(os.path.join(HERE, 'kats_v1.npz')) // 1024, 'KiB')

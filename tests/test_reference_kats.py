@@ -26,6 +26,12 @@ class OracleImpl:
     def combine(self, a, b, mode, ref):
         return self.o.combine(a, b, mode, ref)
 
+    def track_pts(self, flow, ref, pts, int_out=False):
+        return self.o.track_pts(flow, ref, pts, int_out)
+
+    def flow_track(self, fl, pts, status):
+        return self.o.flow_track(fl, pts, False, status)
+
     def flow(self, vecs, ref, mask=None):
         return self.o.OFlow(vecs, ref, mask)
 
@@ -45,6 +51,12 @@ class CudaImpl:
 
     def combine(self, a, b, mode, ref):
         return a.combine(b, mode, ref)
+
+    def track_pts(self, flow, ref, pts, int_out=False):
+        return self.of.track_pts(flow, ref, pts, int_out)
+
+    def flow_track(self, fl, pts, status):
+        return fl.track(pts, get_valid_status=status)
 
     def flow(self, vecs, ref, mask=None):
         return self.of.Flow(vecs.cuda(), ref, None if mask is None else torch.as_tensor(mask).cuda())
@@ -173,3 +185,27 @@ def test_combine_general_refs(impl_cls, mode):
                 else:
                     np.testing.assert_allclose(r.vecs.detach().cpu().numpy(), KATS[k + '_v'], rtol=1e-4, atol=1e-3,
                                                err_msg=k)
+
+
+@pytest.mark.parametrize('impl_cls', IMPLS)
+@pytest.mark.parametrize('ref', ['s', 't'])
+def test_track_pts(impl_cls, ref):
+    """track_pts (reference utils.py:941-1042) and Flow.track (flow_class.py:961-1020): float points
+    (interpolated), integer points (gathered), int_out, 2-D points, validity status, gradients to flow and points."""
+    im = impl_cls()
+    flow, pf, pi, gp = T('trk_flow').to(im.dev), T('trk_pf').to(im.dev), T('trk_pi').to(im.dev), T('trk_gp').to(im.dev)
+    f2, p2 = flow.clone().requires_grad_(), pf.clone().requires_grad_()
+    w = im.track_pts(f2, ref, p2)
+    w.backward(gp)
+    tol = dict(rtol=0, atol=0) if (im.dev == 'cpu' and ref == 's') else dict(rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(w.detach().cpu().numpy(), KATS['trk_%s_f' % ref], **tol)
+    np.testing.assert_allclose(f2.grad.cpu().numpy(), KATS['trk_%s_f_gflow' % ref], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(p2.grad.cpu().numpy(), KATS['trk_%s_f_gpts' % ref], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(im.track_pts(flow, ref, pi).cpu().numpy(), KATS['trk_%s_i' % ref], rtol=1e-4, atol=1e-3)
+    wi = im.track_pts(flow, ref, pf, True)
+    assert wi.dtype == torch.int64
+    assert int((wi.cpu() != T('trk_%s_f_int' % ref)).sum()) <= (0 if im.dev == 'cpu' else 1)
+    np.testing.assert_allclose(im.track_pts(flow, ref, pf[0]).cpu().numpy(), KATS['trk_%s_f_2d' % ref], rtol=1e-4, atol=1e-3)
+    wp, st = im.flow_track(im.flow(T('trk_flow'), ref, T('trk_mask')), pf, True)
+    np.testing.assert_allclose(wp.detach().cpu().numpy(), KATS['trk_%s_flowtrack' % ref], rtol=1e-4, atol=1e-3)
+    np.testing.assert_array_equal(st.cpu().numpy(), KATS['trk_%s_status' % ref])
