@@ -95,6 +95,26 @@ int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sign,
                    float *gflow, float *gsrc, int64_t gsrc_bs,
                    int N, int C, int H, int W, void *stream);
 
+/* Windowed W: the flow/out/valid/flow_mask tensors cover an H x W WINDOW located at (window[0], window[1]) = (y0, x0)
+ * of a global field of window[2] x window[3] pixels; coordinates, the round trip and zero padding live in the global
+ * frame.  src / src_mask / gsrc store rows [window[4], window[4]+window[6]) x cols [window[5], window[5]+window[7])
+ * of the global field (src_bs, src_mask_bs, gsrc_bs refer to that stored size); taps outside the stored region read as
+ * zero.  Uses: Flow.apply(padding=[t,b,l,r], cut=True) for 't' flows without materialising a padded flow (reference
+ * flow_class.py:905-918), and row-band sharding of one oversized field with halo rows.  `window` is a
+ * HOST pointer to 8 ints.  Everything else as ofb_warp_t_fwd / ofb_warp_t_bwd. */
+int ofb_warp_t_win_fwd(const float *flow, int64_t flow_bs, float flow_sign,
+                       const float *src, int64_t src_bs,
+                       const uint8_t *src_mask, int64_t src_mask_bs,
+                       const uint8_t *flow_mask, int64_t flow_mask_bs,
+                       float add_flow, float valid_thresh,
+                       float *out, uint8_t *valid,
+                       int N, int C, int H, int W, const int *window, void *stream);
+int ofb_warp_t_win_bwd(const float *flow, int64_t flow_bs, float flow_sign,
+                       const float *src, int64_t src_bs,
+                       const float *gout, float add_flow,
+                       float *gflow, float *gsrc, int64_t gsrc_bs,
+                       int N, int C, int H, int W, const int *window, void *stream);
+
 /* Workspace (in floats) ofb_splat_s_fwd needs for this problem; has_data_mask != 0 iff data_mask will be given. */
 int64_t ofb_splat_s_workspace(int N, int C, int H, int W, int has_data_mask);
 

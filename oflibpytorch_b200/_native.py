@@ -25,6 +25,8 @@ SIGNATURES = {
     'ofb_flow_stats': ([_P, _P, _P, _I, _I, _I, _P], _I),
     'ofb_warp_t_fwd': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P], _I),
     'ofb_warp_t_bwd': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P], _I),
+    'ofb_warp_t_win_fwd': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P, _P], _I),
+    'ofb_warp_t_win_bwd': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P], _I),
     'ofb_splat_s_workspace': ([_I, _I, _I, _I, _I], _L),
     'ofb_splat_s_fwd': ([_P, _P, _L, _I, _F, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _P, _I,
                          _I, _I, _I, _I, _P], _I),

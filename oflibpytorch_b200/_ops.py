@@ -354,6 +354,87 @@ class _SplatFlow(torch.autograd.Function):
         return gflow, gdata, None, None, None, None, None
 
 
+_lib.define("warp_t_win_fwd(Tensor flow, float sign, Tensor? src, Tensor? src_mask, Tensor? flow_mask, float thresh, "
+            "bool want_valid, int[] window) -> (Tensor, Tensor)")
+_lib.define("warp_t_win_bwd(Tensor flow, float sign, Tensor src, Tensor gout, bool need_gflow, bool need_gsrc, "
+            "int[] window) -> (Tensor, Tensor)")
+
+
+def _win_arr(window):
+    if len(window) != 8:
+        raise ValueError("oflibpytorch_b200: window needs 8 integers (y0, x0, gh, gw, sy0, sx0, sh, sw)")
+    return (ctypes.c_int * 8)(*[int(v) for v in window])
+
+
+def _warp_t_win_fwd(flow, sign, src, src_mask, flow_mask, thresh, want_valid, window):
+    require_cuda(flow, "flow")
+    flow = _f32c(flow)
+    src = None if src is None else _f32c(src)
+    src_mask, flow_mask = _maskc(src_mask), _maskc(flow_mask)
+    _, _, h, w = flow.shape
+    sh, sw = int(window[6]), int(window[7])
+    c = 0 if src is None else src.shape[1]
+    if src is not None and tuple(src.shape[-2:]) != (sh, sw):
+        raise ValueError("oflibpytorch_b200: stored source size does not match the window")
+    n = _batch(flow.shape[0], src, src_mask, flow_mask)
+    dev = flow.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
+        valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
+        _call("ofb_warp_t_win_fwd", _p(flow), _bs(flow, n, 2 * h * w), sign,
+              _p(src) if c else None, _bs(src, n, c * sh * sw), _p(src_mask), _bs(src_mask, n, sh * sw),
+              _p(flow_mask), _bs(flow_mask, n, h * w), 0.0, thresh, _p(out) if c else None,
+              _p(valid) if want_valid else None, n, c, h, w, _win_arr(window), _stream())
+    return out, valid
+
+
+def _warp_t_win_bwd(flow, sign, src, gout, need_gflow, need_gsrc, window):
+    require_cuda(flow, "flow")
+    flow, src, gout = _f32c(flow), _f32c(src), _f32c(gout)
+    n, c, h, w = gout.shape
+    sh, sw = int(window[6]), int(window[7])
+    dev = flow.device
+    with torch.cuda.device(dev):
+        gflow = torch.empty((n, 2, h, w) if need_gflow else (0,), dtype=torch.float32, device=dev)
+        gsrc = torch.empty(tuple(src.shape) if need_gsrc else (0,), dtype=torch.float32, device=dev)
+        _call("ofb_warp_t_win_bwd", _p(flow), _bs(flow, n, 2 * h * w), sign, _p(src), _bs(src, n, c * sh * sw),
+              _p(gout), 0.0, _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None,
+              _bs(src, n, c * sh * sw), n, c, h, w, _win_arr(window), _stream())
+    return gflow, gsrc
+
+
+_lib.impl("warp_t_win_fwd", _warp_t_win_fwd, "CUDA")
+_lib.impl("warp_t_win_bwd", _warp_t_win_bwd, "CUDA")
+
+
+class _WarpTWin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, src, src_mask, flow_mask, sign, thresh, want_valid, window):
+        out, valid = _ops.warp_t_win_fwd(flow, sign, src, src_mask, flow_mask, thresh, want_valid, window)
+        ctx.save_for_backward(flow, src)
+        ctx.sign, ctx.window = sign, list(window)
+        ctx.mark_non_differentiable(valid)
+        return out, valid
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, _gvalid):
+        flow, src = ctx.saved_tensors
+        need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gflow = gsrc = None
+        if need_gflow or need_gsrc:
+            gf, gs = _ops.warp_t_win_bwd(flow, ctx.sign, src, gout, need_gflow, need_gsrc, ctx.window)
+            gflow = _reduce_to(gf, flow) if need_gflow else None
+            gsrc = gs if need_gsrc else None
+        return gflow, gsrc, None, None, None, None, None, None
+
+
+def warp_t_win(flow, src, window, src_mask=None, flow_mask=None, sign=1.0, thresh=0.99999, want_valid=False):
+    """Windowed W (see include/oflib_b200.h: ofb_warp_t_win_fwd).  window = (y0, x0, gh, gw, sy0, sx0, sh, sw)."""
+    return _WarpTWin.apply(flow, src, src_mask, flow_mask, float(sign), float(thresh), bool(want_valid),
+                           [int(v) for v in window])
+
+
 _lib.define("sample_pts_fwd(Tensor flow, Tensor pts) -> Tensor")
 _lib.define("sample_pts_bwd(Tensor flow, Tensor pts, Tensor gout, bool need_gflow, bool need_gpts) -> (Tensor, Tensor)")
 

@@ -20,6 +20,16 @@
 
 namespace ofb {
 
+// Windowed coordinate frame (identity for the plain warp).  The flow / output tensors cover a WINDOW of H x W pixels
+// whose top-left corner sits at (y0, x0) of a GLOBAL field of gh x gw pixels; coordinates, the round trip and the
+// zero-padding test live in the global frame.  The stored source covers rows [sy0, sy0+sh) x cols [sx0, sx0+sw) of
+// the global field (taps outside the stored region read as zero).  Two uses: Flow.apply(padding=..., cut=True)
+// without materialising a padded flow (reference flow_class.py:905-918), and row-band spatial sharding of one
+// oversized field with halo rows.
+struct Window {
+    int y0, x0, gh, gw, sy0, sx0, sh, sw;
+};
+
 struct WarpFwdParams {
     const float *flow; int64_t flow_bs; float sign;
     const float *src; int64_t src_bs;
@@ -28,6 +38,7 @@ struct WarpFwdParams {
     float add_flow, thresh;
     float *out; uint8_t *valid;
     int N, C, H, W;
+    Window win;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -54,7 +65,7 @@ struct PixGeom {                 // tap geometry of one output pixel
     bool pnw, pne, psw, pse;     // tap inside the image (zero padding otherwise)
 };
 
-__device__ __forceinline__ PixGeom pix_geom(float ix, float iy, int W, int H)
+__device__ __forceinline__ PixGeom pix_geom(float ix, float iy, const Window &wn)
 {
     PixGeom g;
     const float x0 = floorf(ix), y0 = floorf(iy);
@@ -66,10 +77,13 @@ __device__ __forceinline__ PixGeom pix_geom(float ix, float iy, int W, int H)
     // cvt.rmi.s32.f32 saturates (and maps NaN to 0), so far-away positions become INT_MIN/INT_MAX and fail the
     // unsigned range tests below exactly like the reference's float comparisons x0 >= 0 && x0 <= W-1 do
     const int xi = __float2int_rd(ix), yi = __float2int_rd(iy);
-    const bool bx0 = (unsigned)xi < (unsigned)W, bx1 = (unsigned)(xi + 1) < (unsigned)W;
-    const bool by0 = (unsigned)yi < (unsigned)H, by1 = (unsigned)(yi + 1) < (unsigned)H;
+    const int lx = xi - wn.sx0, ly = yi - wn.sy0;            // position inside the stored source region
+    const bool bx0 = (unsigned)xi < (unsigned)wn.gw && (unsigned)lx < (unsigned)wn.sw;
+    const bool bx1 = (unsigned)(xi + 1) < (unsigned)wn.gw && (unsigned)(lx + 1) < (unsigned)wn.sw;
+    const bool by0 = (unsigned)yi < (unsigned)wn.gh && (unsigned)ly < (unsigned)wn.sh;
+    const bool by1 = (unsigned)(yi + 1) < (unsigned)wn.gh && (unsigned)(ly + 1) < (unsigned)wn.sh;
     g.pnw = bx0 && by0; g.pne = bx1 && by0; g.psw = bx0 && by1; g.pse = bx1 && by1;
-    g.o = (int)((unsigned)yi * (unsigned)W + (unsigned)xi);   // wraps harmlessly for saturated (far away) positions
+    g.o = (int)((unsigned)ly * (unsigned)wn.sw + (unsigned)lx);   // wraps harmlessly for saturated (far away) positions
     return g;
 }
 
@@ -117,7 +131,8 @@ template <int CN, bool WANT_VALID, bool ALL_IN>
 __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const ItemPtrs &ip, const PixGeom &g,
                                                   int pix, float fx, float fy, int c_first, int cn_rt)
 {
-    const int HW = p.H * p.W, W = p.W;
+    const int HW = p.H * p.W;                       // output / flow plane
+    const int HWs = p.win.sh * p.win.sw, W = p.win.sw;   // stored source plane and its row pitch
     if (WANT_VALID) {
         float a, b, c, d;
         if (ip.smask) {
@@ -136,7 +151,7 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
     if (CN > 0) {
 #pragma unroll
         for (int c = 0; c < CN; ++c) {
-            const int e = c * HW + g.o;                                              // one int add per plane
+            const int e = c * HWs + g.o;                                             // one int add per plane
             float a, b, cc, d;
             load_taps<ALL_IN, float>(ip.src + e, ip.src + (e + W), g, a, b, cc, d);
             float r = blend4(g, a, b, cc, d);
@@ -147,7 +162,7 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
     } else {
 #pragma unroll 1
         for (int c = 0; c < cn_rt; ++c) {
-            const int64_t e = (int64_t)c * HW + g.o;
+            const int64_t e = (int64_t)c * HWs + g.o;
             float a, b, cc, d;
             load_taps<ALL_IN, float>(ip.src + e, ip.src + (e + W), g, a, b, cc, d);
             float r = blend4(g, a, b, cc, d);
@@ -174,9 +189,9 @@ __device__ __forceinline__ void warp_pixel(const WarpFwdParams &p, const ItemPtr
 
 __device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, int n, int c_off)
 {
-    const int64_t HW = (int64_t)p.H * p.W;
+    const int64_t HW = (int64_t)p.H * p.W, HWs = (int64_t)p.win.sh * p.win.sw;
     ItemPtrs ip;
-    ip.src = p.src + (int64_t)n * p.src_bs + c_off * HW;
+    ip.src = p.src + (int64_t)n * p.src_bs + c_off * HWs;
     ip.out = p.out + ((int64_t)n * p.C + c_off) * HW;
     ip.smask = p.src_mask ? p.src_mask + (int64_t)n * p.src_mask_bs : nullptr;
     ip.fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
@@ -206,15 +221,15 @@ __global__ void __launch_bounds__(256) warp_t_fwd_direct_kernel(const WarpFwdPar
         fx[r] = __ldg(fl + q);
         fy[r] = __ldg(fl + (HW + q));
     }
-    const float xf = (float)x;
+    const float xf = (float)(x + p.win.x0);
     const ItemPtrs ip = item_ptrs(p, n, 0);
     const int rows = min(kDirRows, p.H - y0);
 #pragma unroll
     for (int r = 0; r < kDirRows; ++r) {
         if (r >= rows) break;
         float ix, iy;
-        sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r), ix, iy);
-        const PixGeom g = pix_geom(ix, iy, p.W, p.H);
+        sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r + p.win.y0), ix, iy);
+        const PixGeom g = pix_geom(ix, iy, p.win);
         warp_pixel<CN, WANT_VALID>(p, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C);
     }
 }
@@ -333,7 +348,7 @@ __global__ void __launch_bounds__(256, 3) warp_t_fwd_staged_kernel(const WarpFwd
             const float fx = __ldg(fl + y * p.W), fy = __ldg(fl + HW + y * p.W);
             float jx, jy;
             sample_pos(cc, fx, fy, xf, (float)y, jx, jy);
-            const PixGeom g = pix_geom(jx, jy, p.W, p.H);
+            const PixGeom g = pix_geom(jx, jy, p.win);
             warp_pixel_direct<CN, VMODE != 0, false>(p, ip, g, y * p.W + x, fx, fy, c_off, CN);
         }
         return;
@@ -420,6 +435,7 @@ struct WarpBwdParams {
     const float *gout; float add_flow;
     float *gflow; float *gsrc; int64_t gsrc_bs;
     int N, C, H, W;
+    Window win;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -470,13 +486,14 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
     const int rows = min(kBwdRows, p.H - y0);          // warp-uniform
 
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
-    const float *src = p.src ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HW : nullptr;
+    const int HWs = p.win.sh * p.win.sw, SW = p.win.sw;   // stored source plane and its row pitch
+    const float *src = p.src ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HWs : nullptr;
     const float *go = p.gout + ((int64_t)n * p.C + c_off) * HW;
-    float *gsrc = GSRC ? p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HW : nullptr;
+    float *gsrc = GSRC ? p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HWs : nullptr;
     float *gf = GFLOW ? p.gflow + (int64_t)n * 2 * HW : nullptr;
     asm volatile("" : "+l"(fl), "+l"(src), "+l"(go), "+l"(gsrc), "+l"(gf));
 
-    const float xf = (float)x;
+    const float xf = (float)(x + p.win.x0);
     float carry[CN];                                   // south-tap sums waiting for the next row
     int carry_o = 0;
     bool carry_ok = false;
@@ -503,8 +520,8 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
         const int pix = y * p.W + xc;
         const float fx = cur.fx, fy = cur.fy;
         float ix, iy;
-        sample_pos(cc, fx, fy, xf, (float)y, ix, iy);
-        PixGeom g = pix_geom(ix, iy, p.W, p.H);
+        sample_pos(cc, fx, fy, xf, (float)(y + p.win.y0), ix, iy);
+        PixGeom g = pix_geom(ix, iy, p.win);
         g.pnw = g.pnw && active; g.pne = g.pne && active; g.psw = g.psw && active; g.pse = g.pse && active;
 
         float gv[CN];
@@ -515,9 +532,9 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
             float gix = 0.0f, giy = 0.0f;
 #pragma unroll
             for (int c = 0; c < CN; ++c) {
-                const int e = c * HW + g.o;
+                const int e = c * HWs + g.o;
                 float a, b, cq, d;
-                load_taps<false, float>(src + e, src + (e + p.W), g, a, b, cq, d);
+                load_taps<false, float>(src + e, src + (e + SW), g, a, b, cq, d);
                 // d out / d ix and d out / d iy  (SURVEY.md Appendix A.1); gradients carry a tolerance, so FMAs
                 gix = __fmaf_rn(gv[c], __fmaf_rn(b - a, g.sy, (d - cq) * g.ny), gix);
                 giy = __fmaf_rn(gv[c], __fmaf_rn(cq - a, g.ex, (d - b) * g.wx), giy);
@@ -558,22 +575,22 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
                 float top = g.pnw ? g.wnw * gv[c] : 0.0f, bot = g.psw ? g.wsw * gv[c] : 0.0f;
                 if (merge_n) top += p_ne;
                 if (merge_s) bot += p_se;
-                const float *gs = gsrc + c * HW;
+                const float *gs = gsrc + c * HWs;
                 red_add<0>(gs + carry_o, carry[c], flush);
                 if (vmerge) top += carry[c];
                 const float *t = gs + g.o;
                 red_add<0>(t, top, g.pnw);
                 red_add<4>(t, v_ne, east_n);
-                red_add<4>(t + p.W, v_se, east_s);
+                red_add<4>(t + SW, v_se, east_s);
                 carry[c] = bot;
             }
-            carry_o = g.o + p.W;
+            carry_o = g.o + SW;
             carry_ok = g.psw;
         }
     }
     if (GSRC && carry_ok) {
 #pragma unroll
-        for (int c = 0; c < CN; ++c) red_add<0>(gsrc + (c * HW + carry_o), carry[c], true);
+        for (int c = 0; c < CN; ++c) red_add<0>(gsrc + (c * HWs + carry_o), carry[c], true);
     }
 }
 
@@ -601,29 +618,41 @@ static BwdKernel bwd_kernel(int cn, bool gflow, bool gsrc)
 
 using namespace ofb;
 
-extern "C" int ofb_warp_t_fwd(const float *flow, int64_t flow_bs, float flow_sign,
-                              const float *src, int64_t src_bs,
-                              const uint8_t *src_mask, int64_t src_mask_bs,
-                              const uint8_t *flow_mask, int64_t flow_mask_bs,
-                              float add_flow, float valid_thresh,
-                              float *out, uint8_t *valid,
-                              int N, int C, int H, int W, void *stream)
+static bool window_ok(const Window &w, int H, int W)
+{
+    return H >= 1 && W >= 1 && w.gh >= 2 && w.gw >= 2 && w.sh >= 1 && w.sw >= 1 && w.y0 >= 0 && w.x0 >= 0 &&
+           w.y0 + H <= w.gh && w.x0 + W <= w.gw && w.sy0 >= 0 && w.sx0 >= 0 && w.sy0 + w.sh <= w.gh &&
+           w.sx0 + w.sw <= w.gw && (int64_t)w.sh * w.sw <= 0x3fffffff && (int64_t)H * W <= 0x3fffffff;
+}
+
+static bool window_is_identity(const Window &w, int H, int W)
+{
+    return w.y0 == 0 && w.x0 == 0 && w.gh == H && w.gw == W && w.sy0 == 0 && w.sx0 == 0 && w.sh == H && w.sw == W;
+}
+
+static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
+                           const float *src, int64_t src_bs,
+                           const uint8_t *src_mask, int64_t src_mask_bs,
+                           const uint8_t *flow_mask, int64_t flow_mask_bs,
+                           float add_flow, float valid_thresh,
+                           float *out, uint8_t *valid,
+                           int N, int C, int H, int W, const Window &win, void *stream)
 {
     if (!flow || N <= 0 || C < 0 || (C > 0 && (!src || !out)) || (C == 0 && !valid)) return OFB_EINVAL;
     if (add_flow != 0.0f && C != 2) return OFB_EINVAL;
-    if (H < 2 || W < 2) return OFB_ESHAPE;
-    if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
+    if (win.gh < 2 || win.gw < 2) return OFB_ESHAPE;
+    if (!window_ok(win, H, W) || N > 65535) return OFB_EINVAL;
     WarpFwdParams p{flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
-                    add_flow, valid_thresh, out, valid, N, C, H, W};
+                    add_flow, valid_thresh, out, valid, N, C, H, W, win};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const CoordCtx cc{{(float)(W - 1), 1.0f / (float)(W - 1)}, {(float)(H - 1), 1.0f / (float)(H - 1)}, flow_sign};
+    const CoordCtx cc{{(float)(win.gw - 1), 1.0f / (float)(win.gw - 1)}, {(float)(win.gh - 1), 1.0f / (float)(win.gh - 1)},
+                      flow_sign};
 
-    // staged (TMA) path: needs a payload, TMA-compatible pitches, and is not worth it for tiny fields
     // Measured on B200 (profiles/): the L1-cached direct kernel beats the staged one on every flow tried (bounding-box
     // staging over-fetches (1+g)^2 for a flow gradient g, and its load->TMA->compute phases do not overlap inside a
     // CTA), so the staged kernel is opt-in (OFB_TMA=1) until it is software-pipelined across tiles.
     static const bool use_tma = getenv("OFB_TMA") != nullptr;
-    bool staged = use_tma && C > 0 && W >= kTileW && H >= kTileH;
+    bool staged = use_tma && C > 0 && W >= kTileW && H >= kTileH && window_is_identity(win, H, W);
     const int vmode = !valid ? 0 : (src_mask ? 2 : 1);
     alignas(64) CUtensorMap mask_map;
     alignas(64) CUtensorMap src_maps[2];          // [0]: groups of kMaxCN channels, [1]: the remainder group
@@ -680,25 +709,27 @@ extern "C" int ofb_warp_t_fwd(const float *flow, int64_t flow_bs, float flow_sig
     return 0;
 }
 
-extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sign,
-                              const float *src, int64_t src_bs,
-                              const float *gout, float add_flow,
-                              float *gflow, float *gsrc, int64_t gsrc_bs,
-                              int N, int C, int H, int W, void *stream)
+static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
+                           const float *src, int64_t src_bs,
+                           const float *gout, float add_flow,
+                           float *gflow, float *gsrc, int64_t gsrc_bs,
+                           int N, int C, int H, int W, const Window &win, void *stream)
 {
     if (!flow || !gout || N <= 0 || C <= 0 || (gflow && !src)) return OFB_EINVAL;
     if (add_flow != 0.0f && C != 2) return OFB_EINVAL;
-    if (H < 2 || W < 2) return OFB_ESHAPE;
-    if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
+    if (win.gh < 2 || win.gw < 2) return OFB_ESHAPE;
+    if (!window_ok(win, H, W) || N > 65535) return OFB_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!gflow && !gsrc) return 0;
-    const CoordCtx cc{{(float)(W - 1), 1.0f / (float)(W - 1)}, {(float)(H - 1), 1.0f / (float)(H - 1)}, flow_sign};
+    const CoordCtx cc{{(float)(win.gw - 1), 1.0f / (float)(win.gw - 1)}, {(float)(win.gh - 1), 1.0f / (float)(win.gh - 1)},
+                      flow_sign};
     // Optional L2-resident accumulation (OFB_BWD_CHUNK_MB > 0): walk the batch in chunks whose gradient image fits the
     // L2, zero-filling each chunk right before its kernel so the REDs hit L2-resident lines (-24 B/pixel of DRAM
     // traffic).  Measured on B200: a LOSS as separate launches (1.47 -> 1.58/1.75/1.88 ms at 96/48/24 MB chunks,
     // tails and launch gaps dominate), hence off by default; it needs the zero-fill fused into one persistent kernel.
     static const long chunk_mb = getenv("OFB_BWD_CHUNK_MB") ? atol(getenv("OFB_BWD_CHUNK_MB")) : 0;
-    const int64_t item_bytes = (int64_t)C * H * W * 4;
+    const int64_t src_plane = (int64_t)win.sh * win.sw, out_plane = (int64_t)H * W;
+    const int64_t item_bytes = (int64_t)C * src_plane * 4;
     int chunk = N;
     if (gsrc && gsrc_bs != 0 && chunk_mb > 0) {
         chunk = (int)((chunk_mb << 20) / item_bytes);
@@ -716,8 +747,8 @@ extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sig
             if (e != cudaSuccess) return (int)e;
         }
         WarpBwdParams p{flow + (int64_t)n0 * flow_bs, flow_bs, flow_sign, src ? src + (int64_t)n0 * src_bs : nullptr, src_bs,
-                        gout + (int64_t)n0 * C * H * W, add_flow, gflow ? gflow + (int64_t)n0 * 2 * H * W : nullptr,
-                        gsrc ? gsrc + (int64_t)n0 * gsrc_bs : nullptr, gsrc_bs, nn, C, H, W};
+                        gout + (int64_t)n0 * C * out_plane, add_flow, gflow ? gflow + (int64_t)n0 * 2 * out_plane : nullptr,
+                        gsrc ? gsrc + (int64_t)n0 * gsrc_bs : nullptr, gsrc_bs, nn, C, H, W, win};
         const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), nn);
         for (int c0 = 0; c0 < C; c0 += kMaxCN) {       // channel groups of <= 4; gflow accumulates across groups
             const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
@@ -726,4 +757,55 @@ extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sig
         }
     }
     return 0;
+}
+
+extern "C" int ofb_warp_t_fwd(const float *flow, int64_t flow_bs, float flow_sign,
+                              const float *src, int64_t src_bs,
+                              const uint8_t *src_mask, int64_t src_mask_bs,
+                              const uint8_t *flow_mask, int64_t flow_mask_bs,
+                              float add_flow, float valid_thresh,
+                              float *out, uint8_t *valid,
+                              int N, int C, int H, int W, void *stream)
+{
+    if (H < 2 || W < 2) return OFB_ESHAPE;
+    return warp_t_fwd_impl(flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
+                           add_flow, valid_thresh, out, valid, N, C, H, W, Window{0, 0, H, W, 0, 0, H, W}, stream);
+}
+
+extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sign,
+                              const float *src, int64_t src_bs,
+                              const float *gout, float add_flow,
+                              float *gflow, float *gsrc, int64_t gsrc_bs,
+                              int N, int C, int H, int W, void *stream)
+{
+    if (H < 2 || W < 2) return OFB_ESHAPE;
+    return warp_t_bwd_impl(flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W,
+                           Window{0, 0, H, W, 0, 0, H, W}, stream);
+}
+
+// Windowed variants: window[8] = {y0, x0, global_h, global_w, src_y0, src_x0, src_h, src_w} (see struct Window).
+extern "C" int ofb_warp_t_win_fwd(const float *flow, int64_t flow_bs, float flow_sign,
+                                  const float *src, int64_t src_bs,
+                                  const uint8_t *src_mask, int64_t src_mask_bs,
+                                  const uint8_t *flow_mask, int64_t flow_mask_bs,
+                                  float add_flow, float valid_thresh,
+                                  float *out, uint8_t *valid,
+                                  int N, int C, int H, int W, const int *window, void *stream)
+{
+    if (!window) return OFB_EINVAL;
+    const Window w{window[0], window[1], window[2], window[3], window[4], window[5], window[6], window[7]};
+    return warp_t_fwd_impl(flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
+                           add_flow, valid_thresh, out, valid, N, C, H, W, w, stream);
+}
+
+extern "C" int ofb_warp_t_win_bwd(const float *flow, int64_t flow_bs, float flow_sign,
+                                  const float *src, int64_t src_bs,
+                                  const float *gout, float add_flow,
+                                  float *gflow, float *gsrc, int64_t gsrc_bs,
+                                  int N, int C, int H, int W, const int *window, void *stream)
+{
+    if (!window) return OFB_EINVAL;
+    const Window w{window[0], window[1], window[2], window[3], window[4], window[5], window[6], window[7]};
+    return warp_t_bwd_impl(flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, w,
+                           stream);
 }

@@ -382,6 +382,12 @@ class Flow(object):
             raise ValueError("Error applying flow: Flow and target have to have the same shape")
 
         need_valid = return_flow or return_valid_area
+        if padding is not None and cut and self._ref == 't':
+            # Fused padding: the flow is a window at (top, left) of the target's frame; the kernel
+            # works in that frame directly, so neither the zero-padded flow (flow_class.py:913) nor the cut
+            # (flow_class.py:917-918) is materialised.
+            return self._finish_apply(*self._warp_window(t, mask, need_valid, padding), target if return_flow else None,
+                                      return_dtype, return_2d, return_3d, return_valid_area)
         flow = self
         top = left = 0
         if padding is not None:                                     # flow_class.py:905-914
@@ -418,8 +424,30 @@ class Flow(object):
             else:
                 valid = valid & self._mask
 
-        if return_flow:
-            return Flow._make(warped[:, :2].contiguous(), target._ref, valid.contiguous())
+        return self._finish_apply(warped, valid, target if return_flow else None, return_dtype, return_2d, return_3d,
+                                  return_valid_area)
+
+    def _warp_window(self, t: torch.Tensor, mask: Optional[torch.Tensor], need_valid: bool, padding: list):
+        """'t' warp of the (top, left) window of a larger target, with apply_flow's zero-flow early-out."""
+        top, left = padding[0], padding[2]
+        fh, fw = self.shape[1], self.shape[2]
+        th, tw = t.shape[-2:]
+        if self._all_zero(thresholded=True, masked=False):           # utils.py:497-498, then the cut
+            out = t[..., top:top + fh, left:left + fw]
+            valid = None
+            if need_valid:
+                n = max(t.shape[0], self.shape[0])
+                valid = (mask[..., top:top + fh, left:left + fw] if mask is not None else
+                         torch.ones((n, fh, fw), dtype=torch.bool, device=self._device)) & self._mask
+            return out, valid
+        out, valid = _ops.warp_t_win(self._vecs, t, [top, left, th, tw, 0, 0, th, tw], mask if need_valid else None,
+                                     self._mask if need_valid else None, want_valid=need_valid)
+        return out, (valid if need_valid else None)
+
+    def _finish_apply(self, warped, valid, flow_target, return_dtype, return_2d, return_3d, return_valid_area):
+        """Common tail of apply: wrap / round / squeeze (reference flow_class.py:937-959)."""
+        if flow_target is not None:
+            return Flow._make(warped[:, :2].contiguous(), flow_target._ref, valid.contiguous())
         if not return_dtype.is_floating_point:                      # flow_class.py:943-949
             warped = torch.round(warped.float())
             if return_dtype == torch.uint8:

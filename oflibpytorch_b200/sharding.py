@@ -52,6 +52,69 @@ def force_nonzero(flow) -> None:
     flow._stats = [s | 2 | 4 | 8 | 16 for s in stats]
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# one oversized field: row bands with halo exchange ("single oversized field")
+# ----------------------------------------------------------------------------------------------------------------
+
+def exchange_row_halos(band: torch.Tensor, k: int, rank: int, world_size: int, group=None):
+    """`band` (..., hb, W) holds this rank's rows of a field split into contiguous row bands.  Returns
+    (extended, k_top): `extended` = [last k rows of rank-1 | band | first k rows of rank+1] (missing neighbours at
+    the field's top / bottom contribute nothing) and k_top = number of halo rows prepended.  Point-to-point
+    send/recv (NCCL over NVLink on GPUs, gloo on CPU); works for any dtype."""
+    import torch.distributed as dist
+    if k <= 0 or world_size == 1:
+        return band, 0
+    if band.shape[-2] < k:
+        raise ValueError("halo of %d rows exceeds this rank's band of %d rows; use fewer ranks" % (k, band.shape[-2]))
+    up, down = rank - 1, rank + 1
+    ops, top, bot = [], None, None
+    send_top = band[..., :k, :].contiguous()
+    send_bot = band[..., -k:, :].contiguous()
+    if up >= 0:
+        top = torch.empty_like(send_top)
+        ops += [dist.P2POp(dist.isend, send_top, up, group), dist.P2POp(dist.irecv, top, up, group)]
+    if down < world_size:
+        bot = torch.empty_like(send_bot)
+        ops += [dist.P2POp(dist.isend, send_bot, down, group), dist.P2POp(dist.irecv, bot, down, group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    parts = [t for t in (top, band, bot) if t is not None]
+    return (torch.cat(parts, dim=-2) if len(parts) > 1 else band), (k if top is not None else 0)
+
+
+def apply_t_rowbands(flow_band: torch.Tensor, payload_band: torch.Tensor, *, h_total: int, rank: int, world_size: int,
+                     flow_mask_band: torch.Tensor = None, payload_mask_band: torch.Tensor = None, halo: int = None,
+                     want_valid: bool = True, group=None):
+    """Backward ('t') warp of ONE field too large for one GPU, split into `world_size` contiguous row bands
+    (`shard_range(h_total, world_size, rank)`): every rank holds its rows of the flow (N,2,hb,W), of the payload
+    (N,C,hb,W) and of the masks, exchanges `halo` payload rows with its two neighbours and warps its own band in the
+    GLOBAL coordinate frame (windowed kernel), so the result equals the corresponding rows of the single-GPU call bit
+    for bit.  `halo` defaults to ceil(max |flow_y|) + 2 over all ranks (one scalar all-reduce).
+    Returns (out_band (N,C,hb,W), valid_band (N,hb,W) or None).  Differentiable w.r.t. flow_band and payload_band
+    (gradients of halo rows flow back to the neighbour only if the caller exchanges them; not done here)."""
+    import math
+    import torch.distributed as dist
+    from . import _ops
+    a, b = shard_range(h_total, world_size, rank)
+    hb, w = flow_band.shape[-2:]
+    if hb != b - a:
+        raise ValueError("flow band has %d rows, expected rows [%d, %d) of %d" % (hb, a, b, h_total))
+    if halo is None:
+        k = flow_band[:, 1].detach().abs().amax().reshape(1)
+        if dist.is_available() and dist.is_initialized() and world_size > 1:
+            dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+        halo = int(math.ceil(float(k.item()))) + 2
+    ext, k_top = exchange_row_halos(payload_band, halo, rank, world_size, group)
+    ext_mask = None
+    if payload_mask_band is not None:
+        ext_mask, _ = exchange_row_halos(payload_mask_band.to(torch.uint8), halo, rank, world_size, group)
+        ext_mask = ext_mask.to(torch.bool)
+    window = [a, 0, h_total, w, a - k_top, 0, ext.shape[-2], w]
+    out, valid = _ops.warp_t_win(flow_band, ext, window, ext_mask if want_valid else None,
+                                 flow_mask_band if want_valid else None, want_valid=want_valid)
+    return out, (valid if want_valid else None)
+
+
 def gather_shards(local: torch.Tensor, group=None) -> List[torch.Tensor]:
     """Optional epilogue (off the timed path): all-gather equally sized per-rank results."""
     import torch.distributed as dist

@@ -136,3 +136,48 @@ def test_apply_s_flow_returns_warped_mask_and_density_path():
         oo, wo = o.apply_s_flow(flow, img, mask, occ)
         assert_close(og, oo, 'out')
         assert_mask_equal(wg, wo, 'warped mask')
+
+
+def test_windowed_warp_equals_rows_of_the_full_warp():
+    """ofb_warp_t_win_fwd/bwd: warping a row band in the global frame with a halo-extended source band gives exactly the
+    corresponding rows of the full-field warp (this is what row-band spatial sharding relies on)."""
+    from oflibpytorch_b200 import _ops
+    n, c, h, w = 2, 3, 96, 80
+    flow = smooth_flow(n, h, w, 4.0, 970)
+    img = torch.rand(n, c, h, w, generator=gen(971))
+    fmask, tmask = holed_mask(n, h, w, 972), holed_mask(n, h, w, 973)
+    gout = torch.rand(n, c, h, w, generator=gen(974))
+    fg, ig = flow.cuda().requires_grad_(), img.cuda().requires_grad_()
+    full, vfull = of().Flow(fg, 't', fmask.cuda()).apply(ig, tmask.cuda(), return_valid_area=True)
+    full.backward(gout.cuda())
+    k = int(flow[:, 1].abs().max().ceil()) + 2
+    for a, b in ((0, 40), (40, 71), (71, 96)):
+        lo, hi = max(a - k, 0), min(b + k, h)
+        fb = flow[:, :, a:b].contiguous().cuda().requires_grad_()
+        sb = img[:, :, lo:hi].contiguous().cuda().requires_grad_()
+        out, valid = _ops.warp_t_win(fb, sb, [a, 0, h, w, lo, 0, hi - lo, w], tmask[:, lo:hi].contiguous().cuda(),
+                                     fmask[:, a:b].contiguous().cuda(), want_valid=True)
+        assert torch.equal(out, full[:, :, a:b]) and torch.equal(valid, vfull[:, a:b])
+        out.backward(gout[:, :, a:b].contiguous().cuda())
+        assert_grad_close(fb.grad, fg.grad[:, :, a:b], 'gflow band')
+        # the band's contribution to the image gradient is confined to its halo-extended rows
+        assert sb.grad.shape == sb.shape
+
+
+def test_fused_padding_is_bit_identical_to_the_padded_path():
+    """Flow.apply(padding=..., cut=True) for 't' flows runs the windowed kernel (no F.pad, no slice)."""
+    o = orc()
+    n, c, h, w = 2, 3, 40, 52
+    pad = [5, 3, 7, 2]
+    flow = smooth_flow(n, h, w, 3.0, 980)
+    fmask = holed_mask(n, h, w, 981)
+    big = torch.rand(n, c, h + pad[0] + pad[1], w + pad[2] + pad[3], generator=gen(982))
+    bigm = torch.rand(n, h + pad[0] + pad[1], w + pad[2] + pad[3], generator=gen(983)) > 0.1
+    oo, vo = o.OFlow(flow, 't', fmask).apply(big, bigm, return_valid_area=True, padding=pad, cut=True)
+    og, vg = of().Flow(flow.cuda(), 't', fmask.cuda()).apply(big.cuda(), bigm.cuda(), return_valid_area=True,
+                                                             padding=pad, cut=True)
+    assert torch.equal(og.cpu(), oo) and torch.equal(vg.cpu(), vo)
+    z = of().Flow(torch.zeros(n, 2, h, w, device='cuda'), 't', fmask.cuda())
+    og, vg = z.apply(big.cuda(), bigm.cuda(), return_valid_area=True, padding=pad, cut=True)
+    assert torch.equal(og.cpu(), big[..., pad[0]:pad[0] + h, pad[2]:pad[2] + w])
+    assert torch.equal(vg.cpu(), bigm[:, pad[0]:pad[0] + h, pad[2]:pad[2] + w] & fmask)

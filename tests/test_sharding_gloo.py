@@ -87,3 +87,42 @@ def test_sharded_equals_unsharded_world2_gloo():
 def test_agree_all_zero_without_process_group_is_identity():
     from oflibpytorch_b200.sharding import agree_all_zero
     assert agree_all_zero(True) is True and agree_all_zero(False) is False
+
+
+def _halo_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oflibpytorch_b200.sharding import exchange_row_halos, shard_range
+        h, w, k = 23, 7, 3
+        full = torch.arange(2 * 3 * h * w, dtype=torch.float32).view(2, 3, h, w)
+        a, b = shard_range(h, world, rank)
+        ext, k_top = exchange_row_halos(full[:, :, a:b].contiguous(), k, rank, world)
+        lo, hi = max(a - k, 0), min(b + k, h)
+        ok = torch.equal(ext, full[:, :, lo:hi]) and k_top == a - lo
+        m = (full[0, 0] % 2 == 0)
+        em, _ = exchange_row_halos(m[a:b].to(torch.uint8).contiguous(), k, rank, world)
+        ok = ok and torch.equal(em.bool(), m[lo:hi])
+        res = [None] * world
+        dist.all_gather_object(res, bool(ok))
+        if rank == 0:
+            q.put('ok' if all(res) else 'halo mismatch %r' % (res,))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_exchange_row_halos_gloo(world):
+    """Halo rows of a row-band split field: every rank ends up with exactly rows [a-k, b+k) of the full field."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert q.get(timeout=5) == 'ok'
