@@ -161,6 +161,27 @@ int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_bs, int rela
  * generic scalar-gather kernel runs). */
 int64_t ofb_splat_s_bwd_workspace(int N, int C, int H, int W);
 
+/* Row-band splat for ONE field shared by several GPUs: the H x W tensors are rows
+ * [band[0], band[0]+H) of a global field of band[1] rows; the accumulator holds global rows [band[2], band[2]+band[3])
+ * as (N, band[3], W, KP) floats, KP = ofb_splat_s_kp(C, data_mask != NULL) (0: payload too wide).  accumulate
+ * zero-fills and fills the accumulator (targets outside its rows are dropped: size the halo for the flow); the caller
+ * adds the neighbours' halo rows (P2P) and then calls normalise for its own rows.  Arguments as ofb_splat_s_fwd;
+ * `band` is a HOST pointer to 4 ints. */
+int ofb_splat_s_kp(int C, int has_data_mask);
+int ofb_splat_s_band_accumulate(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
+                                const float *data, int64_t data_bs,
+                                const uint8_t *data_mask, int64_t data_mask_bs,
+                                const uint8_t *flow_mask, int64_t flow_mask_bs,
+                                int occlude_zero, float *acc, int N, int C, int H, int W, const int *band, void *stream);
+int ofb_splat_s_band_normalise(const float *cx, const float *cy, int64_t coord_bs, int relative,
+                               const float *data, int64_t data_bs,
+                               const uint8_t *data_mask, int64_t data_mask_bs,
+                               const uint8_t *flow_mask, int64_t flow_mask_bs,
+                               int occlude_zero, const float *acc,
+                               float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
+                               uint8_t *valid, int valid_mode,
+                               int N, int C, int H, int W, const int *band, void *stream);
+
 /* Point sampling of a flow field -- the sparse half of track_pts (utils.py:1003-1019): out[n,m,:] = (flow_y, flow_x)
  * bilinearly interpolated at pts[n,m,:] = (y, x) with grid_sample(align_corners=True, zeros) semantics.
  *   flow (N|1, 2, H, W); pts, out (N, M, 2).  The adjoint yields gflow (N|1,2,H,W; zero-filled by the call; stride 0

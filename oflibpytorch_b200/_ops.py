@@ -487,6 +487,53 @@ def sample_pts(flow, pts):
     return _SamplePts.apply(flow, pts)
 
 
+def splat_band_accumulate(flow, data, data_mask, flow_mask, sign, occlude_zero, band):
+    """Row-band splat, step 1 (forward only): returns the interleaved accumulator (N, acc_h, W, KP) of this band.
+    band = (src_y0, global_h, acc_y0, acc_h); see include/oflib_b200.h ofb_splat_s_band_accumulate."""
+    require_cuda(flow, "flow")
+    flow = _f32c(flow.detach())
+    data = None if data is None else _f32c(data.detach())
+    data_mask, flow_mask = _maskc(data_mask), _maskc(flow_mask)
+    _, _, h, w = flow.shape
+    c = 0 if data is None else data.shape[1]
+    n = _batch(flow.shape[0], data, data_mask, flow_mask)
+    kp = int(_native.lib().ofb_splat_s_kp(c, int(data_mask is not None)))
+    if kp == 0:
+        raise ValueError("oflibpytorch_b200: payloads wider than 6 channels are not supported by the row-band splat")
+    hw = h * w
+    with torch.cuda.device(flow.device):
+        acc = torch.empty((n, int(band[3]), w, kp), dtype=torch.float32, device=flow.device)
+        cx, cy = flow[:, 0], flow[:, 1]
+        _call("ofb_splat_s_band_accumulate", _p(cx), _p(cy), 0 if (flow.shape[0] == 1 and n > 1) else 2 * hw, 1, sign,
+              _p(data) if c else None, _bs(data, n, c * hw), _p(data_mask), _bs(data_mask, n, hw),
+              _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(acc), n, c, h, w,
+              (ctypes.c_int * 4)(*[int(v) for v in band]), _stream())
+    return acc
+
+
+def splat_band_normalise(acc, flow, data, data_mask, flow_mask, occlude_zero, valid_mode, band):
+    """Row-band splat, step 2: normalise this rank's own rows from the (halo-summed) accumulator.
+    Returns (out (N,C,H,W), valid (N,H,W) or empty)."""
+    flow = _f32c(flow.detach())
+    data = None if data is None else _f32c(data.detach())
+    data_mask, flow_mask = _maskc(data_mask), _maskc(flow_mask)
+    _, _, h, w = flow.shape
+    c = 0 if data is None else data.shape[1]
+    n = acc.shape[0]
+    hw = h * w
+    want_valid = valid_mode != VALID_NONE
+    with torch.cuda.device(flow.device):
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=flow.device)
+        valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=flow.device)
+        cx, cy = flow[:, 0], flow[:, 1]
+        _call("ofb_splat_s_band_normalise", _p(cx), _p(cy), 0 if (flow.shape[0] == 1 and n > 1) else 2 * hw, 1,
+              _p(data) if c else None, _bs(data, n, c * hw), _p(data_mask), _bs(data_mask, n, hw),
+              _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(acc.contiguous()), _p(out) if c else None,
+              None, None, None, _p(valid) if want_valid else None, valid_mode, n, c, h, w,
+              (ctypes.c_int * 4)(*[int(v) for v in band]), _stream())
+    return out, valid
+
+
 def splat_xy(x, y, data, mask=None):
     """S with absolute coordinates (grid_from_unstructured_data, utils.py:1061).  Returns (out, density)."""
     out, density, _w, _v = _SplatS.apply(x, y, data, None, mask, False, 1.0, False, VALID_NONE)

@@ -56,6 +56,10 @@ struct SplatParams {
     float *acc;
     float *out, *density; uint8_t *warped_mask, *unocc, *valid; int valid_mode;
     int N, C, H, W;
+    // Row-band frame (identity: src_y0 = 0, gh = H, acc_y0 = 0, acc_h = H).  The H x W tensors are rows
+    // [src_y0, src_y0 + H) of a global field of gh rows; the accumulator stores global rows [acc_y0, acc_y0 + acc_h).
+    // Used by the v1 kernels only (spatial sharding of one oversized field).
+    int src_y0, gh, acc_y0, acc_h;
 };
 
 __device__ __forceinline__ void endpoint(const SplatParams &p, int n, int pix, int x, int y,
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
     const float *data = (C > 0) ? p.data + (int64_t)n * p.data_bs : nullptr;
     const uint8_t *dmask = HAS_BAD ? p.data_mask + (int64_t)n * p.data_mask_bs : nullptr;
     const uint8_t *fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
-    float *acc = p.acc + (int64_t)blockIdx.z * HW * KP;  // workspace item = position inside the chunk
+    float *acc = p.acc + (int64_t)blockIdx.z * p.acc_h * p.W * KP;  // workspace item = position inside the chunk
     asm volatile("" : "+l"(cx), "+l"(cy), "+l"(data), "+l"(dmask), "+l"(fmask), "+l"(acc));
 
     AccVec<KP> carry;                                    // south-tap sums waiting for the next source row
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
         bool fm = active;
         if (p.relative) {
             X = __fadd_rn(__fmul_rn(p.sign, fx), (float)x);                  // utils.py:1056-1057
-            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)y);
+            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)(y + p.src_y0));
             if (p.occlude_zero) fm = fm && !is_zero_vec(fx, fy);             // utils.py:1191-1192
         }
         fm = fm && (cur.fmk != 0);
@@ -247,8 +251,10 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
         // and NaN positions fail the range tests / the w > 0 test below)
         const float x0f = floorf(X), y0f = floorf(Y);
         const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
+        const int ly = yi - p.acc_y0;                                       // row inside the stored accumulator
         const bool bx0 = (unsigned)xi < (unsigned)p.W, bx1 = (unsigned)(xi + 1) < (unsigned)p.W;
-        const bool by0 = (unsigned)yi < (unsigned)p.H, by1 = (unsigned)(yi + 1) < (unsigned)p.H;
+        const bool by0 = (unsigned)yi < (unsigned)p.gh && (unsigned)ly < (unsigned)p.acc_h;
+        const bool by1 = (unsigned)(yi + 1) < (unsigned)p.gh && (unsigned)(ly + 1) < (unsigned)p.acc_h;
         const float ax0 = __fsub_rn(__fadd_rn(x0f, 1.0f), X), ax1 = __fsub_rn(X, x0f);
         const float ay0 = __fsub_rn(__fadd_rn(y0f, 1.0f), Y), ay1 = __fsub_rn(Y, y0f);
         const float w_nw = (fm && bx0 && by0) ? __fmul_rn(ay0, ax0) : 0.0f;   // utils.py:1114, 1123
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
         const float w_sw = (fm && bx0 && by1) ? __fmul_rn(ay1, ax0) : 0.0f;
         const float w_se = (fm && bx1 && by1) ? __fmul_rn(ay1, ax1) : 0.0f;
         const bool p_nw = w_nw > 0.0f, p_ne = w_ne > 0.0f, p_sw = w_sw > 0.0f, p_se = w_se > 0.0f;   // adding +0 is a no-op
-        const int o = (int)((unsigned)yi * (unsigned)p.W + (unsigned)xi);
+        const int o = (int)((unsigned)ly * (unsigned)p.W + (unsigned)xi);
 
         const float *d = cur.d;
         const float badf = (HAS_BAD && cur.dm == 0) ? 1.0f : 0.0f;
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(256) splat_normalise_v1_kernel(const SplatPara
     if (x >= p.W || y >= p.H) return;
     const int HW = p.H * p.W;
     const int pix = y * p.W + x;
-    const float *ab = p.acc + ((int64_t)blockIdx.z * HW + pix) * KP;
+    const float *ab = p.acc + ((int64_t)blockIdx.z * p.acc_h * p.W + (int64_t)(y + p.src_y0 - p.acc_y0) * p.W + x) * KP;
     float a[KP];
     if constexpr (KP == 1) {
         a[0] = __ldcg(ab);
@@ -714,7 +720,7 @@ extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_b
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SplatParams p{cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs,
                   flow_mask, flow_mask_bs, occlude_zero, acc, out, density, warped_mask, unocc,
-                  valid, valid_mode, N, C, H, W};
+                  valid, valid_mode, N, C, H, W, 0, H, 0, H};
     SplatV1 k;
     static const bool planar_only = getenv("OFB_SPLAT_PLANAR") != nullptr;
     if (!planar_only && splat_v1(C, data_mask != nullptr, &k)) {
@@ -797,5 +803,65 @@ extern "C" int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_b
         OFB_CHECK_LAUNCH();
         c0 += kMaxC;
     } while (c0 < C);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-band entry points: accumulate and normalise separately, so that accumulator halos can be exchanged between
+// the GPUs that share one oversized field (oflibpytorch_b200/sharding.py)
+// ------------------------------------------------------------------------------------------------
+extern "C" int ofb_splat_s_kp(int C, int has_data_mask)
+{
+    SplatV1 k;
+    return splat_v1(C, has_data_mask != 0, &k) ? k.kp : 0;
+}
+
+// band[4] = {src_y0, global_h, acc_y0, acc_h}; acc = (N, acc_h, W, KP) floats with KP = ofb_splat_s_kp(C, mask),
+// zero-filled by the call
+extern "C" int ofb_splat_s_band_accumulate(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
+                                           const float *data, int64_t data_bs,
+                                           const uint8_t *data_mask, int64_t data_mask_bs,
+                                           const uint8_t *flow_mask, int64_t flow_mask_bs,
+                                           int occlude_zero, float *acc, int N, int C, int H, int W, const int *band,
+                                           void *stream)
+{
+    SplatV1 k;
+    if (!cx || !cy || !acc || !band || N <= 0 || C < 0 || (C > 0 && !data) || H < 1 || W < 1) return OFB_EINVAL;
+    if (occlude_zero && !relative) return OFB_EINVAL;
+    if (!splat_v1(C, data_mask != nullptr, &k)) return OFB_EINVAL;
+    const int src_y0 = band[0], gh = band[1], acc_y0 = band[2], acc_h = band[3];
+    if (src_y0 < 0 || src_y0 + H > gh || acc_y0 < 0 || acc_h < 1 || acc_y0 + acc_h > gh || N > 65535 ||
+        (int64_t)acc_h * W > 0x3fffffff)
+        return OFB_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)N * acc_h * W * k.kp, st);
+    if (e != cudaSuccess) return (int)e;
+    SplatParams p{cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs, flow_mask, flow_mask_bs,
+                  occlude_zero, acc, nullptr, nullptr, nullptr, nullptr, nullptr, 0, N, C, H, W, src_y0, gh, acc_y0, acc_h};
+    k.acc<<<dim3((W + 63) / 64, (H + 4 * kSplatRows - 1) / (4 * kSplatRows), N), 256, 0, st>>>(p, 0);
+    OFB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int ofb_splat_s_band_normalise(const float *cx, const float *cy, int64_t coord_bs, int relative,
+                                          const float *data, int64_t data_bs,
+                                          const uint8_t *data_mask, int64_t data_mask_bs,
+                                          const uint8_t *flow_mask, int64_t flow_mask_bs,
+                                          int occlude_zero, const float *acc,
+                                          float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
+                                          uint8_t *valid, int valid_mode,
+                                          int N, int C, int H, int W, const int *band, void *stream)
+{
+    SplatV1 k;
+    if (!cx || !cy || !acc || !band || N <= 0 || C < 0 || (C > 0 && (!data || !out)) || H < 1 || W < 1) return OFB_EINVAL;
+    if (valid && valid_mode != OFB_VALID_GT && valid_mode != OFB_VALID_EQ1) return OFB_EINVAL;
+    if (!splat_v1(C, data_mask != nullptr, &k)) return OFB_EINVAL;
+    const int src_y0 = band[0], gh = band[1], acc_y0 = band[2], acc_h = band[3];
+    if (src_y0 < acc_y0 || src_y0 + H > acc_y0 + acc_h || acc_y0 + acc_h > gh || N > 65535) return OFB_EINVAL;
+    SplatParams p{cx, cy, coord_bs, relative, 1.0f, data, data_bs, data_mask, data_mask_bs, flow_mask, flow_mask_bs,
+                  occlude_zero, const_cast<float *>(acc), out, density, warped_mask, unocc, valid, valid_mode,
+                  N, C, H, W, src_y0, gh, acc_y0, acc_h};
+    k.norm<<<dim3((W + 31) / 32, (H + 7) / 8, N), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(p, 0);
+    OFB_CHECK_LAUNCH();
     return 0;
 }

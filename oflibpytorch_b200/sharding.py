@@ -115,6 +115,80 @@ def apply_t_rowbands(flow_band: torch.Tensor, payload_band: torch.Tensor, *, h_t
     return out, (valid if want_valid else None)
 
 
+def exchange_add_accumulator_halos(acc: torch.Tensor, k_top: int, k_bot: int, rank: int, world_size: int, group=None):
+    """`acc` (N, k_top + hb + k_bot, W, KP) is this rank's splat accumulator extended by halo rows that belong to its
+    neighbours.  Sends the halo rows to their owners, receives the neighbours' halos for its own first / last rows and
+    adds them in a FIXED order (own + lower neighbour + upper neighbour), so the result does not depend on arrival
+    order.  Returns the accumulator restricted to this rank's own hb rows."""
+    import torch.distributed as dist
+    hb = acc.shape[1] - k_top - k_bot
+    own = acc[:, k_top:k_top + hb]
+    if world_size == 1:
+        return own.contiguous()
+    up, down = rank - 1, rank + 1
+    ops, from_up, from_down = [], None, None
+    # what the neighbours send has the height of THEIR halo on my side; by construction (same k everywhere, clipped
+    # at the field's borders only) that is k rows, bounded by my band
+    if up >= 0:
+        send = acc[:, :k_top].contiguous()                       # my contributions to the band above
+        from_up = torch.empty((acc.shape[0], min(k_top, hb)) + tuple(acc.shape[2:]), dtype=acc.dtype, device=acc.device)
+        ops += [dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, from_up, up, group)]
+    if down < world_size:
+        send = acc[:, k_top + hb:].contiguous()                   # my contributions to the band below
+        from_down = torch.empty((acc.shape[0], min(k_bot, hb)) + tuple(acc.shape[2:]), dtype=acc.dtype, device=acc.device)
+        ops += [dist.P2POp(dist.isend, send, down, group), dist.P2POp(dist.irecv, from_down, down, group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    own = own.clone()
+    if from_up is not None:
+        own[:, :from_up.shape[1]] += from_up
+    if from_down is not None:
+        own[:, hb - from_down.shape[1]:] += from_down
+    return own
+
+
+def apply_s_rowbands(flow_band: torch.Tensor, payload_band: torch.Tensor, *, h_total: int, rank: int, world_size: int,
+                     flow_mask_band: torch.Tensor = None, payload_mask_band: torch.Tensor = None, halo: int = None,
+                     consider_mask: bool = True, want_valid: bool = True, group=None):
+    """Forward ('s') warp of ONE field split into contiguous row bands over `world_size` GPUs -- the splat counterpart
+    of `apply_t_rowbands`, i.e. `Flow(flow,'s',mask).apply(payload, payload_mask, return_valid_area=True)` for a field
+    that does not fit one GPU.  Every rank splats its source rows into a local accumulator extended by `halo` rows on
+    both sides, the halos are exchanged with the two neighbours (P2P over NVLink) and added in a fixed order, and each
+    rank normalises its own rows.  Forward only.  `halo` defaults to ceil(max |flow_y|) + 2 over all ranks.
+    Returns (out_band (N,C,hb,W), valid_band (N,hb,W) or None)."""
+    import math
+    import torch.distributed as dist
+    from . import _ops
+    a, b = shard_range(h_total, world_size, rank)
+    hb, w = flow_band.shape[-2:]
+    if hb != b - a:
+        raise ValueError("flow band has %d rows, expected rows [%d, %d) of %d" % (hb, a, b, h_total))
+    if halo is None:
+        k = flow_band[:, 1].detach().abs().amax().reshape(1)
+        if dist.is_available() and dist.is_initialized() and world_size > 1:
+            dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+        halo = int(math.ceil(float(k.item()))) + 2
+    if world_size > 1 and halo > hb:
+        raise ValueError("halo of %d rows exceeds this rank's band of %d rows; use fewer ranks" % (halo, hb))
+    lo, hi = max(a - halo, 0), min(b + halo, h_total)
+    fm = flow_mask_band
+    dm = payload_mask_band
+    if want_valid:                                                   # flow_class.py:880-895: target mask AND flow mask
+        if fm is not None:
+            dm = fm if dm is None else (dm & fm)
+        if consider_mask and dm is fm:
+            dm = None                                                # "bad weight" slot provably zero
+    else:
+        dm = None
+    flow_mask_used = fm if consider_mask else None
+    band = (a, h_total, lo, hi - lo)
+    acc = _ops.splat_band_accumulate(flow_band, payload_band, dm, flow_mask_used, 1.0, True, band)
+    own = exchange_add_accumulator_halos(acc, a - lo, hi - b, rank, world_size, group)
+    out, valid = _ops.splat_band_normalise(own, flow_band, payload_band, dm, flow_mask_used, True,
+                                           _ops.VALID_GT if want_valid else _ops.VALID_NONE, (a, h_total, a, hb))
+    return out, (valid if want_valid else None)
+
+
 def gather_shards(local: torch.Tensor, group=None) -> List[torch.Tensor]:
     """Optional epilogue (off the timed path): all-gather equally sized per-rank results."""
     import torch.distributed as dist

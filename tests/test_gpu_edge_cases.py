@@ -181,3 +181,33 @@ def test_fused_padding_is_bit_identical_to_the_padded_path():
     og, vg = z.apply(big.cuda(), bigm.cuda(), return_valid_area=True, padding=pad, cut=True)
     assert torch.equal(og.cpu(), big[..., pad[0]:pad[0] + h, pad[2]:pad[2] + w])
     assert torch.equal(vg.cpu(), bigm[:, pad[0]:pad[0] + h, pad[2]:pad[2] + w] & fmask)
+
+
+def test_row_band_splat_equals_rows_of_the_full_splat():
+    """ofb_splat_s_band_accumulate / _normalise: splatting row bands into halo-extended accumulators, adding the halos
+    and normalising per band reproduces the full-field 's' warp (single GPU emulation of the multi-GPU scheme)."""
+    from oflibpytorch_b200 import _ops
+    n, c, h, w = 2, 3, 90, 72
+    flow = smooth_flow(n, h, w, 4.0, 990)
+    flow[:, :, 30:40, 10:30] = 0.0
+    img = torch.rand(n, c, h, w, generator=gen(991))
+    fmask, tmask = holed_mask(n, h, w, 992), holed_mask(n, h, w, 993)
+    full, vfull = of().Flow(flow.cuda(), 's', fmask.cuda()).apply(img.cuda(), tmask.cuda(), return_valid_area=True)
+    k = int(flow[:, 1].abs().max().ceil()) + 2
+    bands = [(0, 35), (35, 61), (61, 90)]
+    dm = (tmask & fmask).cuda()
+    accs = []
+    for a, b in bands:
+        lo, hi = max(a - k, 0), min(b + k, h)
+        accs.append((lo, hi, _ops.splat_band_accumulate(flow[:, :, a:b].contiguous().cuda(), img[:, :, a:b].contiguous().cuda(),
+                                                         dm[:, a:b].contiguous(), fmask[:, a:b].contiguous().cuda(), 1.0,
+                                                         True, (a, h, lo, hi - lo))))
+    total = torch.zeros((n, h, w, accs[0][2].shape[-1]), device='cuda')
+    for lo, hi, acc in accs:                                   # fixed order: band 0, 1, 2
+        total[:, lo:hi] += acc
+    for a, b in bands:
+        out, valid = _ops.splat_band_normalise(total[:, a:b].contiguous(), flow[:, :, a:b].contiguous().cuda(),
+                                               img[:, :, a:b].contiguous().cuda(), dm[:, a:b].contiguous(),
+                                               fmask[:, a:b].contiguous().cuda(), True, _ops.VALID_GT, (a, h, a, b - a))
+        assert_close(out, full[:, :, a:b], 'band out')
+        assert_mask_equal(valid, vfull[:, a:b], 'band valid')

@@ -105,6 +105,21 @@ def _halo_worker(rank, world, port, q):
         m = (full[0, 0] % 2 == 0)
         em, _ = exchange_row_halos(m[a:b].to(torch.uint8).contiguous(), k, rank, world)
         ok = ok and torch.equal(em.bool(), m[lo:hi])
+        # accumulator halos: every rank holds partial sums for rows [a-k, b+k); after the exchange-add each rank's own
+        # rows must equal the sum over ALL ranks' partials (integers, so the sum is exact in fp32)
+        from oflibpytorch_b200.sharding import exchange_add_accumulator_halos
+        kp = 4
+        def partial(r):
+            aa, bb = shard_range(h, world, r)
+            l2, h2 = max(aa - k, 0), min(bb + k, h)
+            g = torch.Generator().manual_seed(100 + r)
+            t = torch.zeros(2, h, w, kp)
+            t[:, l2:h2] = torch.randint(0, 50, (2, h2 - l2, w, kp), generator=g).float()
+            return t, l2, h2
+        mine, l2, h2 = partial(rank)
+        own = exchange_add_accumulator_halos(mine[:, l2:h2].contiguous(), a - l2, h2 - b, rank, world)
+        total = sum(partial(r)[0] for r in range(world))
+        ok = ok and torch.equal(own, total[:, a:b])
         res = [None] * world
         dist.all_gather_object(res, bool(ok))
         if rank == 0:
