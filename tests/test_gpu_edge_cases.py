@@ -211,3 +211,35 @@ def test_row_band_splat_equals_rows_of_the_full_splat():
                                                fmask[:, a:b].contiguous().cuda(), True, _ops.VALID_GT, (a, h, a, b - a))
         assert_close(out, full[:, :, a:b], 'band out')
         assert_mask_equal(valid, vfull[:, a:b], 'band valid')
+
+
+def test_chained_combine_apply_backward_matches_oracle():
+    """BASELINE.json config 5 at test scale: acc = acc.combine_with(f_i, 3); img_i = acc.apply(img, valid area);
+    loss = sum_i <g_i, img_i>; ONE backward through the whole chain -> gradients of every frame's flow and of the image."""
+    o, m = orc(), of()
+    frames, c, h, w = 5, 3, 48, 64
+    flows = [smooth_flow(1, h, w, 2.0, 1100 + i) for i in range(frames)]
+    img = torch.rand(1, c, h, w, generator=gen(1200))
+    gs = [torch.rand(1, c, h, w, generator=gen(1300 + i)) for i in range(frames)]
+
+    def run(flow_cls, dev, apply_kw):
+        fl = [f.detach().clone().to(dev).requires_grad_() for f in flows]
+        im = img.detach().clone().to(dev).requires_grad_()
+        acc, loss, valids = None, 0.0, []
+        for i in range(frames):
+            cur = flow_cls(fl[i], 't')
+            acc = cur if acc is None else acc.combine_with(cur, 3)
+            out, valid = acc.apply(im, return_valid_area=True)
+            loss = loss + (out * gs[i].to(dev)).sum()
+            valids.append(valid)
+        loss.backward()
+        return acc, valids, [f.grad for f in fl], im.grad
+
+    acc_o, val_o, gf_o, gi_o = run(o.OFlow, 'cpu', {})
+    acc_g, val_g, gf_g, gi_g = run(m.Flow, 'cuda', {})
+    assert_close(acc_g.vecs, acc_o.vecs, 'chained flow')
+    assert_mask_equal(acc_g.mask, acc_o.mask, 'chained mask')
+    for i in range(frames):
+        assert_mask_equal(val_g[i], val_o[i], 'valid %d' % i)
+        assert_grad_close(gf_g[i], gf_o[i], 'gflow %d' % i)
+    assert_grad_close(gi_g, gi_o, 'gimg')
