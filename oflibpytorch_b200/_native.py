@@ -53,6 +53,8 @@ def lib():
                 "There is no CPU or PyTorch fallback." % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
         for name, (argtypes, restype) in SIGNATURES.items():
+            if not hasattr(handle, name) and os.environ.get('OFB_SKIP_ABI_TABLE'):
+                continue                                  # tuning aid only: A/B against an older build
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = restype

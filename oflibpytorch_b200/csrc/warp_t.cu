@@ -65,6 +65,7 @@ struct PixGeom {                 // tap geometry of one output pixel
     bool pnw, pne, psw, pse;     // tap inside the image (zero padding otherwise)
 };
 
+template <bool WIN>
 __device__ __forceinline__ PixGeom pix_geom(float ix, float iy, const Window &wn)
 {
     PixGeom g;
@@ -77,11 +78,12 @@ __device__ __forceinline__ PixGeom pix_geom(float ix, float iy, const Window &wn
     // cvt.rmi.s32.f32 saturates (and maps NaN to 0), so far-away positions become INT_MIN/INT_MAX and fail the
     // unsigned range tests below exactly like the reference's float comparisons x0 >= 0 && x0 <= W-1 do
     const int xi = __float2int_rd(ix), yi = __float2int_rd(iy);
-    const int lx = xi - wn.sx0, ly = yi - wn.sy0;            // position inside the stored source region
-    const bool bx0 = (unsigned)xi < (unsigned)wn.gw && (unsigned)lx < (unsigned)wn.sw;
-    const bool bx1 = (unsigned)(xi + 1) < (unsigned)wn.gw && (unsigned)(lx + 1) < (unsigned)wn.sw;
-    const bool by0 = (unsigned)yi < (unsigned)wn.gh && (unsigned)ly < (unsigned)wn.sh;
-    const bool by1 = (unsigned)(yi + 1) < (unsigned)wn.gh && (unsigned)(ly + 1) < (unsigned)wn.sh;
+    // WIN = false (compile time): the stored source IS the global field, no second range test, no origin shift
+    const int lx = WIN ? xi - wn.sx0 : xi, ly = WIN ? yi - wn.sy0 : yi;   // position inside the stored source region
+    const bool bx0 = (unsigned)xi < (unsigned)wn.gw && (!WIN || (unsigned)lx < (unsigned)wn.sw);
+    const bool bx1 = (unsigned)(xi + 1) < (unsigned)wn.gw && (!WIN || (unsigned)(lx + 1) < (unsigned)wn.sw);
+    const bool by0 = (unsigned)yi < (unsigned)wn.gh && (!WIN || (unsigned)ly < (unsigned)wn.sh);
+    const bool by1 = (unsigned)(yi + 1) < (unsigned)wn.gh && (!WIN || (unsigned)(ly + 1) < (unsigned)wn.sh);
     g.pnw = bx0 && by0; g.pne = bx1 && by0; g.psw = bx0 && by1; g.pse = bx1 && by1;
     g.o = (int)((unsigned)ly * (unsigned)wn.sw + (unsigned)lx);   // wraps harmlessly for saturated (far away) positions
     return g;
@@ -128,11 +130,11 @@ struct ItemPtrs {
 // One output pixel through global memory: channels [0, CN) (CN = 0: cn_rt channels, runtime loop).
 // pix = y*W + x of the output pixel; c_first = absolute index of channel 0 (for add_flow).
 template <int CN, bool WANT_VALID, bool ALL_IN>
-__device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const ItemPtrs &ip, const PixGeom &g,
-                                                  int pix, float fx, float fy, int c_first, int cn_rt)
+__device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const Window &wn, const ItemPtrs &ip,
+                                                  const PixGeom &g, int pix, float fx, float fy, int c_first, int cn_rt)
 {
     const int HW = p.H * p.W;                       // output / flow plane
-    const int HWs = p.win.sh * p.win.sw, W = p.win.sw;   // stored source plane and its row pitch
+    const int HWs = wn.sh * wn.sw, W = wn.sw;       // stored source plane and its row pitch
     if (WANT_VALID) {
         float a, b, c, d;
         if (ip.smask) {
@@ -176,20 +178,20 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
 // dispatch on the warp-uniform "every tap of every lane is inside the image" predicate (true for all but the
 // warps that sample near the image border)
 template <int CN, bool WANT_VALID>
-__device__ __forceinline__ void warp_pixel(const WarpFwdParams &p, const ItemPtrs &ip, const PixGeom &g,
+__device__ __forceinline__ void warp_pixel(const WarpFwdParams &p, const Window &wn, const ItemPtrs &ip, const PixGeom &g,
                                            int pix, float fx, float fy, int c_first, int cn_rt)
 {
 #ifdef OFB_ALLIN_FASTPATH
     if (__all_sync(__activemask(), g.pnw && g.pne && g.psw && g.pse))
-        warp_pixel_direct<CN, WANT_VALID, true>(p, ip, g, pix, fx, fy, c_first, cn_rt);
+        warp_pixel_direct<CN, WANT_VALID, true>(p, wn, ip, g, pix, fx, fy, c_first, cn_rt);
     else
 #endif
-        warp_pixel_direct<CN, WANT_VALID, false>(p, ip, g, pix, fx, fy, c_first, cn_rt);
+        warp_pixel_direct<CN, WANT_VALID, false>(p, wn, ip, g, pix, fx, fy, c_first, cn_rt);
 }
 
-__device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, int n, int c_off)
+__device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, const Window &wn, int n, int c_off)
 {
-    const int64_t HW = (int64_t)p.H * p.W, HWs = (int64_t)p.win.sh * p.win.sw;
+    const int64_t HW = (int64_t)p.H * p.W, HWs = (int64_t)wn.sh * wn.sw;
     ItemPtrs ip;
     ip.src = p.src + (int64_t)n * p.src_bs + c_off * HWs;
     ip.out = p.out + ((int64_t)n * p.C + c_off) * HW;
@@ -202,10 +204,16 @@ __device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, int n, int
     return ip;
 }
 
-constexpr int kDirRows = 4;    // rows per thread; CTA tile = 64 x 16 (2 warps across x, 4 across y)
+#ifndef OFB_FWD_ROWS
+#define OFB_FWD_ROWS 4
+#endif
+#ifndef OFB_FWD_MINB
+#define OFB_FWD_MINB 8
+#endif
+constexpr int kDirRows = OFB_FWD_ROWS;    // rows per thread; CTA tile = 64 x 4*rows (2 warps across x, 4 across y)
 
-template <int CN, bool WANT_VALID>
-__global__ void __launch_bounds__(256) warp_t_fwd_direct_kernel(const WarpFwdParams p, const CoordCtx cc)
+template <int CN, bool WANT_VALID, bool WIN>
+__global__ void __launch_bounds__(256, OFB_FWD_MINB) warp_t_fwd_direct_kernel(const WarpFwdParams p, const CoordCtx cc)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
@@ -221,16 +229,18 @@ __global__ void __launch_bounds__(256) warp_t_fwd_direct_kernel(const WarpFwdPar
         fx[r] = __ldg(fl + q);
         fy[r] = __ldg(fl + (HW + q));
     }
-    const float xf = (float)(x + p.win.x0);
-    const ItemPtrs ip = item_ptrs(p, n, 0);
+    // identity window: built from H, W so that everything folds to the plain-warp code at compile time
+    const Window wn = WIN ? p.win : Window{0, 0, p.H, p.W, 0, 0, p.H, p.W};
+    const float xf = (float)(x + wn.x0);
+    const ItemPtrs ip = item_ptrs(p, wn, n, 0);
     const int rows = min(kDirRows, p.H - y0);
 #pragma unroll
     for (int r = 0; r < kDirRows; ++r) {
         if (r >= rows) break;
         float ix, iy;
-        sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r + p.win.y0), ix, iy);
-        const PixGeom g = pix_geom(ix, iy, p.win);
-        warp_pixel<CN, WANT_VALID>(p, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C);
+        sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r + wn.y0), ix, iy);
+        const PixGeom g = pix_geom<WIN>(ix, iy, wn);
+        warp_pixel<CN, WANT_VALID>(p, wn, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C);
     }
 }
 
@@ -339,7 +349,8 @@ __global__ void __launch_bounds__(256, 3) warp_t_fwd_staged_kernel(const WarpFwd
     if (mode == 1) {   // footprint larger than the box: this tile goes through global memory
         if (x >= p.W) return;
         const float *fl = p.flow + (int64_t)n * p.flow_bs + x;
-        ItemPtrs ip = item_ptrs(p, n, c_off);
+        const Window wn{0, 0, p.H, p.W, 0, 0, p.H, p.W};
+        ItemPtrs ip = item_ptrs(p, wn, n, c_off);
         if (VMODE != 2) ip.smask = nullptr;
 #pragma unroll 1
         for (int r = 0; r < kRows; ++r) {            // positions are recomputed: keeps this cold path small
@@ -348,8 +359,8 @@ __global__ void __launch_bounds__(256, 3) warp_t_fwd_staged_kernel(const WarpFwd
             const float fx = __ldg(fl + y * p.W), fy = __ldg(fl + HW + y * p.W);
             float jx, jy;
             sample_pos(cc, fx, fy, xf, (float)y, jx, jy);
-            const PixGeom g = pix_geom(jx, jy, p.win);
-            warp_pixel_direct<CN, VMODE != 0, false>(p, ip, g, y * p.W + x, fx, fy, c_off, CN);
+            const PixGeom g = pix_geom<false>(jx, jy, wn);
+            warp_pixel_direct<CN, VMODE != 0, false>(p, wn, ip, g, y * p.W + x, fx, fy, c_off, CN);
         }
         return;
     }
@@ -472,7 +483,7 @@ __device__ __forceinline__ void red_add(const float *a, float v, bool pred)
                                                                    // the clobber would pin every load behind the REDs
 }
 
-template <int CN, bool GFLOW, bool GSRC>
+template <int CN, bool GFLOW, bool GSRC, bool WIN>
 __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
                                                          const int accumulate_gflow)
 {
@@ -486,14 +497,15 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
     const int rows = min(kBwdRows, p.H - y0);          // warp-uniform
 
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
-    const int HWs = p.win.sh * p.win.sw, SW = p.win.sw;   // stored source plane and its row pitch
+    const Window wn = WIN ? p.win : Window{0, 0, p.H, p.W, 0, 0, p.H, p.W};
+    const int HWs = wn.sh * wn.sw, SW = wn.sw;   // stored source plane and its row pitch
     const float *src = p.src ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HWs : nullptr;
     const float *go = p.gout + ((int64_t)n * p.C + c_off) * HW;
     float *gsrc = GSRC ? p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HWs : nullptr;
     float *gf = GFLOW ? p.gflow + (int64_t)n * 2 * HW : nullptr;
     asm volatile("" : "+l"(fl), "+l"(src), "+l"(go), "+l"(gsrc), "+l"(gf));
 
-    const float xf = (float)(x + p.win.x0);
+    const float xf = (float)(x + wn.x0);
     float carry[CN];                                   // south-tap sums waiting for the next row
     int carry_o = 0;
     bool carry_ok = false;
@@ -520,8 +532,8 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
         const int pix = y * p.W + xc;
         const float fx = cur.fx, fy = cur.fy;
         float ix, iy;
-        sample_pos(cc, fx, fy, xf, (float)(y + p.win.y0), ix, iy);
-        PixGeom g = pix_geom(ix, iy, p.win);
+        sample_pos(cc, fx, fy, xf, (float)(y + wn.y0), ix, iy);
+        PixGeom g = pix_geom<WIN>(ix, iy, wn);
         g.pnw = g.pnw && active; g.pne = g.pne && active; g.psw = g.psw && active; g.pse = g.pse && active;
 
         float gv[CN];
@@ -596,21 +608,21 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
 
 typedef void (*BwdKernel)(const WarpBwdParams, const CoordCtx, const int, const int);
 
-template <int CN>
+template <int CN, bool WIN>
 static BwdKernel bwd_kernel_for(bool gflow, bool gsrc)
 {
-    if (gflow && gsrc) return warp_t_bwd_kernel<CN, true, true>;
-    if (gflow) return warp_t_bwd_kernel<CN, true, false>;
-    return warp_t_bwd_kernel<CN, false, true>;
+    if (gflow && gsrc) return warp_t_bwd_kernel<CN, true, true, WIN>;
+    if (gflow) return warp_t_bwd_kernel<CN, true, false, WIN>;
+    return warp_t_bwd_kernel<CN, false, true, WIN>;
 }
 
-static BwdKernel bwd_kernel(int cn, bool gflow, bool gsrc)
+static BwdKernel bwd_kernel(int cn, bool gflow, bool gsrc, bool win)
 {
     switch (cn) {
-        case 1: return bwd_kernel_for<1>(gflow, gsrc);
-        case 2: return bwd_kernel_for<2>(gflow, gsrc);
-        case 3: return bwd_kernel_for<3>(gflow, gsrc);
-        default: return bwd_kernel_for<4>(gflow, gsrc);
+        case 1: return win ? bwd_kernel_for<1, true>(gflow, gsrc) : bwd_kernel_for<1, false>(gflow, gsrc);
+        case 2: return win ? bwd_kernel_for<2, true>(gflow, gsrc) : bwd_kernel_for<2, false>(gflow, gsrc);
+        case 3: return win ? bwd_kernel_for<3, true>(gflow, gsrc) : bwd_kernel_for<3, false>(gflow, gsrc);
+        default: return win ? bwd_kernel_for<4, true>(gflow, gsrc) : bwd_kernel_for<4, false>(gflow, gsrc);
     }
 }
 
@@ -691,19 +703,21 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     {
         const dim3 grid((W + 63) / 64, (H + 4 * kDirRows - 1) / (4 * kDirRows), N);
         const bool wv = valid != nullptr;
-        switch (C) {
-            case 0: warp_t_fwd_direct_kernel<0, true><<<grid, 256, 0, st>>>(p, cc); break;
-            case 1: if (wv) warp_t_fwd_direct_kernel<1, true><<<grid, 256, 0, st>>>(p, cc);
-                    else warp_t_fwd_direct_kernel<1, false><<<grid, 256, 0, st>>>(p, cc); break;
-            case 2: if (wv) warp_t_fwd_direct_kernel<2, true><<<grid, 256, 0, st>>>(p, cc);
-                    else warp_t_fwd_direct_kernel<2, false><<<grid, 256, 0, st>>>(p, cc); break;
-            case 3: if (wv) warp_t_fwd_direct_kernel<3, true><<<grid, 256, 0, st>>>(p, cc);
-                    else warp_t_fwd_direct_kernel<3, false><<<grid, 256, 0, st>>>(p, cc); break;
-            case 4: if (wv) warp_t_fwd_direct_kernel<4, true><<<grid, 256, 0, st>>>(p, cc);
-                    else warp_t_fwd_direct_kernel<4, false><<<grid, 256, 0, st>>>(p, cc); break;
-            default: if (wv) warp_t_fwd_direct_kernel<0, true><<<grid, 256, 0, st>>>(p, cc);
-                     else warp_t_fwd_direct_kernel<0, false><<<grid, 256, 0, st>>>(p, cc); break;
+        typedef void (*DirectKernel)(const WarpFwdParams, const CoordCtx);
+        DirectKernel k;
+        const int cn = (C >= 1 && C <= 4) ? C : 0;     // 0 = runtime channel loop (also C == 0: validity only)
+#define OFB_PICK(CN_) (wv || C == 0 ? (win_id ? warp_t_fwd_direct_kernel<CN_, true, false> : warp_t_fwd_direct_kernel<CN_, true, true>) \
+                                    : (win_id ? warp_t_fwd_direct_kernel<CN_, false, false> : warp_t_fwd_direct_kernel<CN_, false, true>))
+        const bool win_id = window_is_identity(win, H, W);
+        switch (cn) {
+            case 1: k = OFB_PICK(1); break;
+            case 2: k = OFB_PICK(2); break;
+            case 3: k = OFB_PICK(3); break;
+            case 4: k = OFB_PICK(4); break;
+            default: k = OFB_PICK(0); break;
         }
+#undef OFB_PICK
+        k<<<grid, 256, 0, st>>>(p, cc);
     }
     OFB_CHECK_LAUNCH();
     return 0;
@@ -752,7 +766,8 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
         const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), nn);
         for (int c0 = 0; c0 < C; c0 += kMaxCN) {       // channel groups of <= 4; gflow accumulates across groups
             const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
-            bwd_kernel(cn, gflow != nullptr, gsrc != nullptr)<<<grid, 256, 0, st>>>(p, cc, c0, c0 > 0 ? 1 : 0);
+            bwd_kernel(cn, gflow != nullptr, gsrc != nullptr, !window_is_identity(win, H, W))<<<grid, 256, 0, st>>>(
+                p, cc, c0, c0 > 0 ? 1 : 0);
             OFB_CHECK_LAUNCH();
         }
     }
