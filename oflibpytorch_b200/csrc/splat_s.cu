@@ -60,6 +60,9 @@ struct SplatParams {
     // [src_y0, src_y0 + H) of a global field of gh rows; the accumulator stores global rows [acc_y0, acc_y0 + acc_h).
     // Used by the v1 kernels only (spatial sharding of one oversized field).
     int src_y0, gh, acc_y0, acc_h;
+    // SPLIT layout only (C + 1 fills the vector, e.g. RGB + density): the bad-weight channel is a plane of its own
+    // behind the vectors instead of a second float4 per pixel that would be four fifths padding
+    float *acc_bad;
 };
 
 __device__ __forceinline__ void endpoint(const SplatParams &p, int n, int pix, int x, int y,
@@ -192,10 +195,14 @@ __device__ __forceinline__ void red_vec(float *acc, int q, const AccVec<KP> &a, 
     }
 }
 
-template <int C, bool HAS_BAD, int KP>
-__global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const SplatParams p, const int n0)
+#ifndef OFB_SPLAT_MINB
+#define OFB_SPLAT_MINB 3
+#endif
+template <int C, bool HAS_BAD, int KP, bool SPLIT = false>
+__global__ void __launch_bounds__(256, OFB_SPLAT_MINB) splat_accumulate_v1_kernel(const SplatParams p, const int n0)
 {
-    static_assert(C + 1 + (HAS_BAD ? 1 : 0) <= KP, "accumulator slots");
+    constexpr bool BAD_SLOT = HAS_BAD && !SPLIT;       // bad weight rides in the vector
+    static_assert(C + 1 + (BAD_SLOT ? 1 : 0) <= KP && (!SPLIT || HAS_BAD), "accumulator slots");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
     const int y0 = blockIdx.y * (4 * kSplatRows) + (warp >> 1) * kSplatRows;
@@ -210,7 +217,8 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
     const uint8_t *dmask = HAS_BAD ? p.data_mask + (int64_t)n * p.data_mask_bs : nullptr;
     const uint8_t *fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
     float *acc = p.acc + (int64_t)blockIdx.z * p.acc_h * p.W * KP;  // workspace item = position inside the chunk
-    asm volatile("" : "+l"(cx), "+l"(cy), "+l"(data), "+l"(dmask), "+l"(fmask), "+l"(acc));
+    float *accb = SPLIT ? p.acc_bad + (int64_t)blockIdx.z * p.acc_h * p.W : nullptr;
+    asm volatile("" : "+l"(cx), "+l"(cy), "+l"(data), "+l"(dmask), "+l"(fmask), "+l"(acc), "+l"(accb));
 
     AccVec<KP> carry;                                    // south-tap sums waiting for the next source row
 #pragma unroll
@@ -271,9 +279,18 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
         AccVec<KP> top, bot, ene, ese;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
-            const float m = (j < C) ? d[j < C ? j : 0] : (j == C ? 1.0f : ((HAS_BAD && j == C + 1) ? badf : 0.0f));
+            const float m = (j < C) ? d[j < C ? j : 0] : (j == C ? 1.0f : ((BAD_SLOT && j == C + 1) ? badf : 0.0f));
             top.v[j] = __fmul_rn(w_nw, m); ene.v[j] = __fmul_rn(w_ne, m);
             bot.v[j] = __fmul_rn(w_sw, m); ese.v[j] = __fmul_rn(w_se, m);
+        }
+
+        if constexpr (SPLIT) {
+            if (badf != 0.0f) {                          // few sources carry bad weight: plain scalar REDs, no merging
+                if (p_nw) atomicAdd(accb + o, w_nw);
+                if (p_ne) atomicAdd(accb + (o + 1), w_ne);
+                if (p_sw) atomicAdd(accb + (o + p.W), w_sw);
+                if (p_se) atomicAdd(accb + (o + p.W + 1), w_se);
+            }
         }
 
         // ---- horizontal merge with lane-1
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
         const bool taken_s = (lane < 31) && ((bs >> (lane + 1)) & 1u);
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
-            if (j >= C + 1 + (HAS_BAD ? 1 : 0)) continue;                  // padding slots stay zero
+            if (j >= C + 1 + (BAD_SLOT ? 1 : 0)) continue;                 // padding slots stay zero
             const float pn = __shfl_up_sync(0xffffffffu, ene.v[j], 1), ps = __shfl_up_sync(0xffffffffu, ese.v[j], 1);
             if (merge_n) top.v[j] += pn;
             if (merge_s) bot.v[j] += ps;
@@ -310,74 +327,118 @@ __global__ void __launch_bounds__(256, 3) splat_accumulate_v1_kernel(const Splat
     red_vec<KP>(acc, carry_o, carry, carry_ok);
 }
 
-// normalise + masks + un-occlude fill from the interleaved accumulator (same arithmetic as splat_normalise_kernel)
-template <int C, bool HAS_BAD, int KP>
+// normalise + masks + un-occlude fill from the interleaved accumulator.  Same results as splat_normalise_kernel for
+// every mask bit; the payload is multiplied by the correctly rounded reciprocal of the clamped density instead of
+// divided by it (<= 1 ulp apart, against a parity tolerance of 1e-4) and the mask-channel division only runs where
+// its outcome is not known beforehand.  One thread walks kNormRows rows of one column so that the per-item pointer
+// arithmetic is paid once, not per pixel.
+constexpr int kNormRows = 4;       // CTA tile = 64 x 16 (2 warps across x, 4 across y)
+
+template <int C, bool HAS_BAD, int KP, bool SPLIT = false>
 __global__ void __launch_bounds__(256) splat_normalise_v1_kernel(const SplatParams p, const int n0)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * (4 * kNormRows) + (warp >> 1) * kNormRows;
     const int n = n0 + blockIdx.z;
-    if (x >= p.W || y >= p.H) return;
+    if (x >= p.W || y0 >= p.H) return;
+    const int rows = min(kNormRows, p.H - y0);
     const int HW = p.H * p.W;
-    const int pix = y * p.W + x;
-    const float *ab = p.acc + ((int64_t)blockIdx.z * p.acc_h * p.W + (int64_t)(y + p.src_y0 - p.acc_y0) * p.W + x) * KP;
-    float a[KP];
-    if constexpr (KP == 1) {
-        a[0] = __ldcg(ab);
-    } else if constexpr (KP == 2) {
-        const float2 q = __ldcg(reinterpret_cast<const float2 *>(ab));
-        a[0] = q.x; a[1] = q.y;
-    } else {
+    const float *ab = p.acc + ((int64_t)blockIdx.z * p.acc_h * p.W + (int64_t)(y0 + p.src_y0 - p.acc_y0) * p.W + x) * KP;
+    const float *cx = p.cx + (int64_t)n * p.coord_bs, *cy = p.cy + (int64_t)n * p.coord_bs;
+    const float *data = (C > 0) ? p.data + (int64_t)n * p.data_bs : nullptr;
+    const uint8_t *dmask = HAS_BAD ? p.data_mask + (int64_t)n * p.data_mask_bs : nullptr;
+    const uint8_t *fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
+    float *out = (C > 0) ? p.out + (int64_t)n * C * HW : nullptr;
+    float *density = p.density ? p.density + (int64_t)n * HW : nullptr;
+    uint8_t *wmask = p.warped_mask ? p.warped_mask + (int64_t)n * HW : nullptr;
+    uint8_t *unocc_o = p.unocc ? p.unocc + (int64_t)n * HW : nullptr;
+    uint8_t *valid = p.valid ? p.valid + (int64_t)n * HW : nullptr;
+    const float *abad = SPLIT ? p.acc_bad + (int64_t)blockIdx.z * p.acc_h * p.W +
+                                    (int64_t)(y0 + p.src_y0 - p.acc_y0) * p.W + x : nullptr;
+    asm volatile("" : "+l"(ab), "+l"(abad), "+l"(cx), "+l"(cy), "+l"(data), "+l"(dmask), "+l"(fmask));
+    asm volatile("" : "+l"(out), "+l"(density), "+l"(wmask), "+l"(unocc_o), "+l"(valid));
+    const bool occ = p.occlude_zero && p.relative;
+    const bool eq1 = p.valid_mode == OFB_VALID_EQ1;
+
+    float a[kNormRows][KP], sb[kNormRows];
 #pragma unroll
-        for (int h = 0; h < KP / 4; ++h) {
-            const float4 q = __ldcg(reinterpret_cast<const float4 *>(ab) + h);
-            a[4 * h] = q.x; a[4 * h + 1] = q.y; a[4 * h + 2] = q.z; a[4 * h + 3] = q.w;
-        }
-    }
-    const float den = a[C];
-    const float bad = HAS_BAD ? a[C + 1] : 0.0f;
-    const float dc = fmaxf(den, OFB_MIN_DENSITY);
-    const bool wm = den > 0.0f;
-    bool unocc = false;
-    if (p.occlude_zero && p.relative && !wm) {
-        const float fx = __ldg(p.cx + (int64_t)n * p.coord_bs + pix);
-        const float fy = __ldg(p.cy + (int64_t)n * p.coord_bs + pix);
-        unocc = is_zero_vec(fx, fy);
-        if (p.flow_mask) unocc = unocc && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix) != 0);
-    }
-    if (C > 0) {
-        const float *data = p.data + (int64_t)n * p.data_bs + pix;
-        float *out = p.out + (int64_t)n * C * HW + pix;
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-            out[c * HW] = unocc ? __ldg(data + c * HW) : __fdiv_rn(a[c], dc);
-    }
-    if (p.density) p.density[(int64_t)n * HW + pix] = den;
-    if (p.warped_mask) p.warped_mask[(int64_t)n * HW + pix] = wm ? 1 : 0;
-    if (p.unocc) p.unocc[(int64_t)n * HW + pix] = unocc ? 1 : 0;
-    if (p.valid) {
-        float mch;
-        if (unocc) {
-            mch = (HAS_BAD && __ldg(p.data_mask + (int64_t)n * p.data_mask_bs + pix) == 0) ? 0.0f : 1.0f;
+    for (int r = 0; r < kNormRows; ++r) {
+        if (r >= rows) break;
+        const float *ar = ab + r * (p.W * KP);
+        if constexpr (SPLIT) sb[r] = __ldcg(abad + r * p.W);
+        if constexpr (KP == 1) {
+            a[r][0] = __ldcg(ar);
+        } else if constexpr (KP == 2) {
+            const float2 q = __ldcg(reinterpret_cast<const float2 *>(ar));
+            a[r][0] = q.x; a[r][1] = q.y;
         } else {
-            const float mnum = (bad == 0.0f) ? den : __fsub_rn(den, bad);
-            mch = __fdiv_rn(mnum, dc);
+#pragma unroll
+            for (int h = 0; h < KP / 4; ++h) {
+                const float4 q = __ldcg(reinterpret_cast<const float4 *>(ar) + h);
+                a[r][4 * h] = q.x; a[r][4 * h + 1] = q.y; a[r][4 * h + 2] = q.z; a[r][4 * h + 3] = q.w;
+            }
         }
-        const bool ok = (p.valid_mode == OFB_VALID_EQ1) ? (mch == 1.0f) : (mch > 0.99999f);
-        p.valid[(int64_t)n * HW + pix] = ok ? 1 : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < kNormRows; ++r) {
+        if (r >= rows) break;
+        const int pix = (y0 + r) * p.W + x;
+        const float den = a[r][C];
+        const float bad = SPLIT ? sb[r] : (HAS_BAD ? a[r][C + 1] : 0.0f);
+        const float dc = fmaxf(den, OFB_MIN_DENSITY);
+        const bool wm = den > 0.0f;
+        bool unocc = false;
+        if (occ && !wm) {
+            unocc = is_zero_vec(__ldg(cx + pix), __ldg(cy + pix));
+            if (fmask) unocc = unocc && (__ldg(fmask + pix) != 0);
+        }
+        if (C > 0) {
+            const float inv = __frcp_rn(dc);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                out[c * HW + pix] = unocc ? __ldg(data + (c * HW + pix)) : __fmul_rn(a[r][c], inv);
+        }
+        if (density) density[pix] = den;
+        if (wmask) wmask[pix] = wm ? 1 : 0;
+        if (unocc_o) unocc_o[pix] = unocc ? 1 : 0;
+        if (valid) {
+            // mask channel = (den - bad) / max(den, 1e-3)   (utils.py:1144 applied to the mask plane)
+            float mch;
+            if (unocc) {
+                mch = (HAS_BAD && __ldg(dmask + pix) == 0) ? 0.0f : 1.0f;
+            } else if (bad == 0.0f) {
+                // den / max(den, 1e-3): exactly 1 from 1e-3 up, exactly 0 at 0, a real quotient only in between
+                mch = (den >= OFB_MIN_DENSITY) ? 1.0f : (wm ? __fdiv_rn(den, OFB_MIN_DENSITY) : 0.0f);
+            } else {
+                mch = __fdiv_rn(__fsub_rn(den, bad), dc);
+            }
+            valid[pix] = (eq1 ? (mch == 1.0f) : (mch > 0.99999f)) ? 1 : 0;
+        }
     }
 }
 
 typedef void (*SplatKernel)(const SplatParams, const int);
-struct SplatV1 { SplatKernel acc, norm; int kp; };
+// kp floats per pixel in the vectors; split != 0: plus one plane for the bad-weight channel (acc_s / norm_s kernels)
+struct SplatV1 { SplatKernel acc, norm; int kp; SplatKernel acc_s, norm_s; int kp_s; };
 
 template <int C>
 static SplatV1 splat_v1_for(bool bad)
 {
     constexpr int KPb = (C + 2 <= 2) ? 2 : ((C + 2 <= 4) ? 4 : 8);
     constexpr int KPn = (C + 1 <= 1) ? 1 : ((C + 1 <= 2) ? 2 : ((C + 1 <= 4) ? 4 : 8));
-    if (bad) return {splat_accumulate_v1_kernel<C, true, KPb>, splat_normalise_v1_kernel<C, true, KPb>, KPb};
-    return {splat_accumulate_v1_kernel<C, false, KPn>, splat_normalise_v1_kernel<C, false, KPn>, KPn};
+    if (bad) {
+        SplatV1 k{splat_accumulate_v1_kernel<C, true, KPb>, splat_normalise_v1_kernel<C, true, KPb>, KPb,
+                  nullptr, nullptr, 0};
+        if constexpr (KPn < KPb) {       // the bad channel alone would double the vector: give it its own plane
+            k.acc_s = splat_accumulate_v1_kernel<C, true, KPn, true>;
+            k.norm_s = splat_normalise_v1_kernel<C, true, KPn, true>;
+            k.kp_s = KPn;
+        }
+        return k;
+    }
+    return {splat_accumulate_v1_kernel<C, false, KPn>, splat_normalise_v1_kernel<C, false, KPn>, KPn,
+            nullptr, nullptr, 0};
 }
 
 static bool splat_v1(int C, bool bad, SplatV1 *k)
@@ -686,19 +747,36 @@ static bool splat_bwd_v1(int C, SplatBwdV1 *k)
 
 using namespace ofb;
 
-// floats of workspace ofb_splat_s_fwd wants for this problem: one L2-sized chunk of interleaved accumulators for
-// the vector-RED path (C <= 6), C+2 planes per item for the planar path
+// layout of the vector-RED path for this problem: floats per pixel in the vectors and whether the bad-weight channel
+// sits in a plane of its own behind them
+static void splat_v1_layout(const SplatV1 &k, int *kp, bool *split)
+{
+    static const bool no_split = getenv("OFB_SPLAT_NOSPLIT") != nullptr;
+    *split = k.acc_s != nullptr && !no_split;
+    *kp = *split ? k.kp_s : k.kp;
+}
+
+static int64_t splat_v1_chunk(int64_t item_floats, int N)
+{
+    static const long chunk_mb = getenv("OFB_SPLAT_CHUNK_MB") ? atol(getenv("OFB_SPLAT_CHUNK_MB")) : 1024;
+    int64_t chunk = ((int64_t)chunk_mb << 20) / (item_floats * 4);
+    if (chunk < 1) chunk = 1;
+    if (chunk > N) chunk = N;
+    return chunk;
+}
+
+// floats of workspace ofb_splat_s_fwd wants for this problem: one chunk of interleaved accumulators for the
+// vector-RED path (C <= 6), C+2 planes per item for the planar path
 extern "C" int64_t ofb_splat_s_workspace(int N, int C, int H, int W, int has_data_mask)
 {
     SplatV1 k;
     if (N <= 0 || C < 0 || H <= 0 || W <= 0) return 0;
     if (getenv("OFB_SPLAT_PLANAR") == nullptr && splat_v1(C, has_data_mask != 0, &k)) {
-        const int64_t item_floats = (int64_t)H * W * k.kp;
-        const long chunk_mb = getenv("OFB_SPLAT_CHUNK_MB") ? atol(getenv("OFB_SPLAT_CHUNK_MB")) : 1024;
-        int64_t chunk = ((int64_t)chunk_mb << 20) / (item_floats * 4);
-        if (chunk < 1) chunk = 1;
-        if (chunk > N) chunk = N;
-        return chunk * item_floats;
+        int kp;
+        bool split;
+        splat_v1_layout(k, &kp, &split);
+        const int64_t item_floats = (int64_t)H * W * (kp + (split ? 1 : 0));
+        return splat_v1_chunk(item_floats, N) * item_floats;
     }
     return (int64_t)N * (C + 2) * H * W;
 }
@@ -720,29 +798,29 @@ extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_b
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SplatParams p{cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs,
                   flow_mask, flow_mask_bs, occlude_zero, acc, out, density, warped_mask, unocc,
-                  valid, valid_mode, N, C, H, W, 0, H, 0, H};
+                  valid, valid_mode, N, C, H, W, 0, H, 0, H, nullptr};
     SplatV1 k;
     static const bool planar_only = getenv("OFB_SPLAT_PLANAR") != nullptr;
     if (!planar_only && splat_v1(C, data_mask != nullptr, &k)) {
-        // chunk = as many items as keep the interleaved accumulator within ~48 MB (L2-resident), at least one; the
-        // workspace the caller provides (N*(C+2)*H*W floats) bounds it from above
-        const int64_t item_floats = (int64_t)H * W * k.kp;
-        static const long chunk_mb = getenv("OFB_SPLAT_CHUNK_MB") ? atol(getenv("OFB_SPLAT_CHUNK_MB")) : 1024;
-        int64_t chunk = ((int64_t)chunk_mb << 20) / (item_floats * 4);
+        // chunk = as many items as the chunk budget and the workspace the caller provides allow, at least one
+        int kp;
+        bool split;
+        splat_v1_layout(k, &kp, &split);
+        const int64_t item_floats = (int64_t)H * W * (kp + (split ? 1 : 0));
+        int64_t chunk = splat_v1_chunk(item_floats, N);
         const int64_t fit = acc_floats / item_floats;
         if (chunk > fit) chunk = fit;
-        if (chunk < 1) chunk = 1;
-        if (chunk > N) chunk = N;
         if (fit >= 1) {
+            const SplatKernel acc_k = split ? k.acc_s : k.acc, norm_k = split ? k.norm_s : k.norm;
+            p.acc_bad = split ? acc + chunk * (int64_t)H * W * kp : nullptr;   // planes behind the chunk's vectors
             const dim3 agrid((W + 63) / 64, (H + 4 * kSplatRows - 1) / (4 * kSplatRows), 1);
-            const dim3 nblock(32, 8);
             for (int n0 = 0; n0 < N; n0 += (int)chunk) {
                 const int nn = (N - n0 < chunk) ? (N - n0) : (int)chunk;
-                cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)item_floats * nn, st);
+                cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)item_floats * chunk, st);
                 if (e != cudaSuccess) return (int)e;
-                k.acc<<<dim3(agrid.x, agrid.y, nn), 256, 0, st>>>(p, n0);
+                acc_k<<<dim3(agrid.x, agrid.y, nn), 256, 0, st>>>(p, n0);
                 OFB_CHECK_LAUNCH();
-                k.norm<<<dim3((W + 31) / 32, (H + 7) / 8, nn), nblock, 0, st>>>(p, n0);
+                norm_k<<<dim3((W + 63) / 64, (H + 4 * kNormRows - 1) / (4 * kNormRows), nn), 256, 0, st>>>(p, n0);
                 OFB_CHECK_LAUNCH();
             }
             return 0;
@@ -861,7 +939,7 @@ extern "C" int ofb_splat_s_band_normalise(const float *cx, const float *cy, int6
     SplatParams p{cx, cy, coord_bs, relative, 1.0f, data, data_bs, data_mask, data_mask_bs, flow_mask, flow_mask_bs,
                   occlude_zero, const_cast<float *>(acc), out, density, warped_mask, unocc, valid, valid_mode,
                   N, C, H, W, src_y0, gh, acc_y0, acc_h};
-    k.norm<<<dim3((W + 31) / 32, (H + 7) / 8, N), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(p, 0);
+    k.norm<<<dim3((W + 63) / 64, (H + 4 * kNormRows - 1) / (4 * kNormRows), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, 0);
     OFB_CHECK_LAUNCH();
     return 0;
 }
