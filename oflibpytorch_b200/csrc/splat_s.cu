@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(256, OFB_SPLAT_MINB) splat_accumulate_v1_kerne
     const bool active = x < p.W;                         // inactive lanes still take part in the shuffles
     const int xc = min(x, p.W - 1);
     const int rows = min(kSplatRows, p.H - y0);          // warp-uniform
+    if (rows <= 0) return;                               // whole warp below the field (the row prefetch must not run)
 
     const float *cx = p.cx + (int64_t)n * p.coord_bs, *cy = p.cy + (int64_t)n * p.coord_bs;
     const float *data = (C > 0) ? p.data + (int64_t)n * p.data_bs : nullptr;

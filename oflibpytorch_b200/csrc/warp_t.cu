@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const War
     const bool active = x < p.W;                       // inactive lanes still take part in the shuffles
     const int xc = min(x, p.W - 1);
     const int rows = min(kBwdRows, p.H - y0);          // warp-uniform
+    if (rows <= 0) return;                             // whole warp below the field (the row prefetch must not run)
 
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
     const Window wn = WIN ? p.win : Window{0, 0, p.H, p.W, 0, 0, p.H, p.W};
