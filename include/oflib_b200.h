@@ -191,6 +191,35 @@ int ofb_sample_pts_fwd(const float *flow, int64_t flow_bs, const float *pts, flo
 int ofb_sample_pts_bwd(const float *flow, int64_t flow_bs, const float *pts, const float *gout,
                        float *gflow, int64_t gflow_bs, float *gpts, int N, int M, int H, int W, void *stream);
 
+/* ---- callers and data formats either side of the path ----------------------------- */
+
+/* Masked extent of the flow end points: extent (N,4) floats = [min_y, max_y, min_x, max_x] of
+ * pos = grid -/+ thresholded(flow) over the pixels where mask is set (mask NULL = all), i.e. the reductions of
+ * Flow.get_padding (flow_class.py:1195-1216) for a whole batch in one pass and one host read.  An item without a
+ * single masked pixel reports [+inf, -inf, +inf, -inf].  is_source_ref != 0 for 's' flows. */
+int ofb_flow_extent(const float *flow, const uint8_t *mask, int is_source_ref, float *extent,
+                    int N, int H, int W, void *stream);
+
+/* Sintel .flo payload, (N,H,W,2) interleaved little-endian floats as they sit in the file after the 12-byte
+ * header, to (N,2,H,W) planes (load_sintel + to_tensor, utils.py:844-855). */
+int ofb_flo_to_planar(const float *interleaved, float *planar, int N, int H, int W, void *stream);
+
+/* KITTI flow png payload, (N,H,W,3) uint16 in the channel order png decoders deliver it with cv2 ([valid, v, u]),
+ * to flow planes (u16 - 2^15) / 64 and a 0/1 valid mask (load_kitti, utils.py:821-829); valid may be NULL. */
+int ofb_kitti_decode(const uint16_t *png_bgr, float *flow, uint8_t *valid, int N, int H, int W, void *stream);
+
+/* Bilinear resize with align_corners = False and the scale factor used for the source index, as
+ * torch.nn.functional.interpolate(scale_factor=...) does it (resize_flow, utils.py:878-916; Flow.resize,
+ * flow_class.py:694-712).  Output extent along each axis = ofb_resize_output_size(in, scale).
+ *   flow (N,2,H,W) -> out (N,2,Ho,Wo) with the x component times scale_x and the y component times scale_y
+ *   mask (N,H,W)   -> out_mask (N,Ho,Wo) = round-half-even of the resized 0/1 mask
+ * Either pair may be NULL.  ofb_resize_bwd is the adjoint of the flow part (gin is zero-filled by the call). */
+int ofb_resize_output_size(int in_size, double scale);
+int ofb_resize_fwd(const float *flow, const uint8_t *mask, double scale_y, double scale_x,
+                   float *out, uint8_t *out_mask, int N, int H, int W, void *stream);
+int ofb_resize_bwd(const float *gout, double scale_y, double scale_x, float *gin,
+                   int N, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _L = ctypes.c_int64
 _F = ctypes.c_float
+_D = ctypes.c_double
 
 # name -> argtypes, exactly the prototypes of include/oflib_b200.h
 SIGNATURES = {
@@ -39,6 +40,12 @@ SIGNATURES = {
                                    _I, _I, _I, _I, _P, _P], _I),
     'ofb_sample_pts_fwd': ([_P, _L, _P, _P, _I, _I, _I, _I, _P], _I),
     'ofb_sample_pts_bwd': ([_P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _P], _I),
+    'ofb_flow_extent': ([_P, _P, _I, _P, _I, _I, _I, _P], _I),
+    'ofb_flo_to_planar': ([_P, _P, _I, _I, _I, _P], _I),
+    'ofb_kitti_decode': ([_P, _P, _P, _I, _I, _I, _P], _I),
+    'ofb_resize_output_size': ([_I, _D], _I),
+    'ofb_resize_fwd': ([_P, _P, _D, _D, _P, _P, _I, _I, _I, _P], _I),
+    'ofb_resize_bwd': ([_P, _D, _D, _P, _I, _I, _I, _P], _I),
 }
 
 

@@ -538,3 +538,116 @@ def splat_xy(x, y, data, mask=None):
     """S with absolute coordinates (grid_from_unstructured_data, utils.py:1061).  Returns (out, density)."""
     out, density, _w, _v = _SplatS.apply(x, y, data, None, mask, False, 1.0, False, VALID_NONE)
     return out, density
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# callers and data formats either side of the path (csrc/ingest.cu)
+# ------------------------------------------------------------------------------------------------------------------
+_lib.define("flow_extent(Tensor flow, Tensor? mask, bool source_ref) -> Tensor")
+_lib.define("flo_to_planar(Tensor interleaved) -> Tensor")
+_lib.define("kitti_decode(Tensor png_bgr, bool want_valid) -> (Tensor, Tensor)")
+_lib.define("resize_fwd(Tensor? flow, Tensor? mask, float scale_y, float scale_x) -> (Tensor, Tensor)")
+_lib.define("resize_bwd(Tensor gout, float scale_y, float scale_x, int h, int w) -> Tensor")
+
+
+def _flow_extent(flow, mask, source_ref):
+    require_cuda(flow, "flow")
+    flow, mask = _f32c(flow), _maskc(mask)
+    n, _, h, w = flow.shape
+    with torch.cuda.device(flow.device):
+        ext = torch.empty((n, 4), dtype=torch.float32, device=flow.device)
+        _call("ofb_flow_extent", _p(flow), _p(mask), int(source_ref), _p(ext), n, h, w, _stream())
+    return ext
+
+
+def _flo_to_planar(interleaved):
+    require_cuda(interleaved, "flow data")
+    x = interleaved if (interleaved.dtype == torch.float32 and interleaved.is_contiguous()) else \
+        interleaved.to(torch.float32).contiguous()
+    n, h, w, _ = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((n, 2, h, w), dtype=torch.float32, device=x.device)
+        _call("ofb_flo_to_planar", _p(x), _p(out), n, h, w, _stream())
+    return out
+
+
+def _kitti_decode(png_bgr, want_valid):
+    require_cuda(png_bgr, "KITTI data")
+    x = png_bgr.contiguous()
+    n, h, w, _ = x.shape
+    with torch.cuda.device(x.device):
+        flow = torch.empty((n, 2, h, w), dtype=torch.float32, device=x.device)
+        valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=x.device)
+        _call("ofb_kitti_decode", _p(x), _p(flow), _p(valid) if want_valid else None, n, h, w, _stream())
+    return flow, valid
+
+
+def _resize_fwd(flow, mask, scale_y, scale_x):
+    t = flow if flow is not None else mask
+    require_cuda(t, "flow")
+    flow = None if flow is None else _f32c(flow)
+    mask = _maskc(mask)
+    n, h, w = t.shape[0], t.shape[-2], t.shape[-1]
+    ho = int(_native.lib().ofb_resize_output_size(h, scale_y))
+    wo = int(_native.lib().ofb_resize_output_size(w, scale_x))
+    with torch.cuda.device(t.device):
+        out = torch.empty((n, 2, ho, wo) if flow is not None else (0,), dtype=torch.float32, device=t.device)
+        out_mask = torch.empty((n, ho, wo) if mask is not None else (0,), dtype=torch.bool, device=t.device)
+        _call("ofb_resize_fwd", _p(flow), _p(mask), scale_y, scale_x, _p(out) if flow is not None else None,
+              _p(out_mask) if mask is not None else None, n, h, w, _stream())
+    return out, out_mask
+
+
+def _resize_bwd(gout, scale_y, scale_x, h, w):
+    require_cuda(gout, "gradient")
+    gout = _f32c(gout)
+    n = gout.shape[0]
+    with torch.cuda.device(gout.device):
+        gin = torch.empty((n, 2, h, w), dtype=torch.float32, device=gout.device)
+        _call("ofb_resize_bwd", _p(gout), scale_y, scale_x, _p(gin), n, h, w, _stream())
+    return gin
+
+
+_lib.impl("flow_extent", _flow_extent, "CUDA")
+_lib.impl("flo_to_planar", _flo_to_planar, "CUDA")
+_lib.impl("kitti_decode", _kitti_decode, "CUDA")
+_lib.impl("resize_fwd", _resize_fwd, "CUDA")
+_lib.impl("resize_bwd", _resize_bwd, "CUDA")
+
+
+class _ResizeFlow(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, scale_y, scale_x):
+        ctx.geom = (scale_y, scale_x, flow.shape[-2], flow.shape[-1])
+        return _ops.resize_fwd(flow, None, scale_y, scale_x)[0]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        sy, sx, h, w = ctx.geom
+        return _ops.resize_bwd(gout, sy, sx, h, w), None, None
+
+
+def flow_extent(flow, mask=None, source_ref=False):
+    """(N,4) = [min_y, max_y, min_x, max_x] of the masked flow end points (flow_class.py:1195-1216)."""
+    return _ops.flow_extent(flow.detach(), mask, bool(source_ref))
+
+
+def flo_to_planar(interleaved):
+    """(N,H,W,2) .flo payload on the device -> (N,2,H,W)."""
+    return _ops.flo_to_planar(interleaved)
+
+
+def kitti_decode(png_bgr, want_valid=True):
+    """(N,H,W,3) uint16 KITTI png payload (cv2 channel order) on the device -> flow (N,2,H,W), valid (N,H,W)."""
+    return _ops.kitti_decode(png_bgr, bool(want_valid))
+
+
+def resize_flow(flow, scale_y, scale_x):
+    """Differentiable bilinear resize of (N,2,H,W) with rescaled vectors (utils.py:906-909)."""
+    return _ResizeFlow.apply(flow, float(scale_y), float(scale_x))
+
+
+def resize_mask(mask, scale_y, scale_x):
+    """round(bilinear resize of the 0/1 mask) as bool (flow_class.py:707-712)."""
+    return _ops.resize_fwd(None, mask, float(scale_y), float(scale_x))[1]

@@ -268,6 +268,53 @@ class Flow(object):
         return self[padding[0]:h - padding[1], padding[2]:w - padding[3]]
 
     # ------------------------------------------------------------------ zero tests
+    # ------------------------------------------------------------------ ingest, resize, padding
+    @classmethod
+    def from_sintel(cls, path: str, inv_path: str = None, device: Union[torch.device, int, str] = None) -> FlowAlias:
+        """Flow with reference 's' from a Sintel ``.flo`` file, optionally with the invalid-pixel ``.png`` as mask
+        (reference flow_class.py:358-373).  `device` defaults to the current CUDA device."""
+        from .utils import load_sintel, load_sintel_mask
+        flow = load_sintel(path, device)
+        mask = None if inv_path is None else load_sintel_mask(inv_path, flow.device)
+        return cls(flow, 's', mask)
+
+    @classmethod
+    def from_kitti(cls, path: str, load_valid: bool = None, device: Union[torch.device, int, str] = None) -> FlowAlias:
+        """Flow with reference 's' from a KITTI uint16 ``.png``, the valid pixels as mask unless `load_valid` is
+        False (reference flow_class.py:331-355).  `device` defaults to the current CUDA device."""
+        from .utils import load_kitti_batch
+        load_valid = True if load_valid is None else load_valid
+        if not isinstance(load_valid, bool):
+            raise TypeError("Error loading flow from KITTI data: Load_valid needs to be boolean")
+        flow, valid = load_kitti_batch([path], device, load_valid)
+        return cls(flow, 's', valid)
+
+    def resize(self, scale: Union[float, int, list, tuple]) -> FlowAlias:
+        """Resized flow with rescaled vectors and the bilinearly resized, rounded mask (reference
+        flow_class.py:694-712); differentiable with respect to the vectors.  Vectors and mask go through one kernel
+        launch each (``ofb_resize_fwd``) instead of two interpolations, two in-place scalings and a round."""
+        from .utils import _valid_scale
+        s = _valid_scale(scale)
+        vecs = _ops.resize_flow(self._vecs, s[0], s[1])
+        mask = _ops.resize_mask(self._mask, s[0], s[1])
+        return Flow(vecs, self._ref, mask)
+
+    def get_padding(self, item: int = None) -> list:
+        """[top, bottom, left, right] per batch item (or for `item`) so that every masked vector finds its source
+        ('t') or keeps its destination ('s') inside the padded area (reference flow_class.py:1174-1224).  The masked
+        min/max of the end points of the whole batch come from one kernel and one host read; the reference does
+        four reductions with a host sync each per item."""
+        flow = self.select(item=item)
+        ext = _ops.flow_extent(flow._vecs, flow._mask, flow._ref == 's').cpu()
+        if bool(torch.isinf(ext).any()):
+            raise RuntimeError("Error determining padding: the mask of a batch item has no valid pixel")
+        h, w = flow.shape[1], flow.shape[2]
+        zero = torch.zeros(())
+        pads = torch.stack((torch.maximum(-ext[:, 0], zero), torch.maximum(ext[:, 1] - (h - 1), zero),
+                            torch.maximum(-ext[:, 2], zero), torch.maximum(ext[:, 3] - (w - 1), zero)), dim=1)
+        padding = [[int(v) for v in row] for row in torch.ceil(pads).tolist()]
+        return padding[0] if item is not None else padding
+
     def _get_stats(self) -> List[int]:
         """Per-item OFB_STAT_* flags of (vecs, mask): one kernel, one sync, cached."""
         if self._stats is None:

@@ -47,3 +47,9 @@ def valid_source(flow: Union[np.ndarray, torch.Tensor], ref: str) -> torch.Tenso
     """reference flow_operations.py:257-277"""
     s = Flow(flow, ref).valid_source()
     return s if len(flow.shape) > 3 else s.squeeze(0)
+
+
+def get_flow_padding(flow: Union[np.ndarray, torch.Tensor], ref: str) -> list:
+    """reference flow_operations.py:280-303"""
+    p = Flow(flow, ref).get_padding()
+    return p if len(flow.shape) > 3 else p[0]

@@ -375,3 +375,129 @@ def track_pts(flow: Union[np.ndarray, torch.Tensor], ref: str, pts: torch.Tensor
     if return_2d:
         warped_pts = warped_pts.squeeze(0)
     return warped_pts
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ingest and resize: the data formats either side of the warp/splat path (reference utils.py:810-916)
+# ------------------------------------------------------------------------------------------------------------------
+def _read_flo_header(path: str):
+    """12-byte Sintel header: tag 'PIEH', width, height as little-endian int32 (utils.py:844-852)."""
+    if not isinstance(path, str):
+        raise TypeError("Error loading flow from Sintel data: Path needs to be a string")
+    with open(path, 'rb') as file:
+        if file.read(4) != b'PIEH':
+            raise ValueError("Error loading flow from Sintel data: Path not a valid .flo file")
+        w, h = int.from_bytes(file.read(4), 'little'), int.from_bytes(file.read(4), 'little')
+    if w < 1 or h < 1:
+        raise ValueError("Error loading flow from Sintel data: Invalid size read from file ('{}', '{}')".format(w, h))
+    return h, w
+
+
+def _ingest_device(device: Any) -> torch.device:
+    """the loaders of this package deliver to the current CUDA device unless told otherwise"""
+    return torch.device('cuda', torch.cuda.current_device()) if device is None else get_valid_device(device)
+
+
+def load_sintel_batch(paths: List[str], device: Any = None) -> torch.Tensor:
+    """B200-native batched form of :func:`load_sintel`: N ``.flo`` files of one size -> (N,2,H,W) fp32 on `device`.
+
+    The payload of every file is read straight into ONE pinned host buffer (no numpy copy, no host-side axis
+    swap), moved with one host-to-device copy and de-interleaved on the device (``ofb_flo_to_planar``).
+    """
+    if not isinstance(paths, (list, tuple)) or len(paths) == 0:
+        raise TypeError("Error loading flow from Sintel data: Paths needs to be a non-empty list of strings")
+    sizes = [_read_flo_header(p) for p in paths]
+    if any(s != sizes[0] for s in sizes):
+        raise ValueError("Error loading flow from Sintel data: All files of a batch need to have the same size")
+    h, w = sizes[0]
+    device = _ingest_device(device)
+    staging = torch.empty((len(paths), h, w, 2), dtype=torch.float32).pin_memory()
+    raw = staging.numpy()
+    for i, p in enumerate(paths):
+        with open(p, 'rb') as file:
+            file.seek(12)
+            got = file.readinto(memoryview(raw[i]).cast('B'))
+        if got != h * w * 8:
+            raise ValueError("Error loading flow from Sintel data: File '{}' is shorter than its header says".format(p))
+    if np.dtype('<f4') != np.dtype('=f4'):                     # the file format is little-endian
+        raw.byteswap(inplace=True)
+    return _ops.flo_to_planar(staging.to(device, non_blocking=True))
+
+
+def load_sintel(path: str, device: Any = None) -> torch.Tensor:
+    """(2,H,W) flow from a Sintel ``.flo`` file (reference utils.py:832-855), on the current CUDA device unless
+    `device` says otherwise."""
+    return load_sintel_batch([path], device)[0]
+
+
+def load_sintel_mask(path: str, device: Any = None) -> torch.Tensor:
+    """(H,W) bool mask of the VALID pixels from a Sintel invalid-pixel ``.png`` (reference utils.py:858-875).
+    The png decode is host work (cv2, as in the reference); the tensor lands on the CUDA device."""
+    import cv2
+    if not isinstance(path, str):
+        raise TypeError("Error loading flow from Sintel data: Path needs to be a string")
+    mask = cv2.imread(path, 0)
+    if mask is None:
+        raise ValueError("Error loading flow from Sintel data: Invalid mask could not be loaded from path")
+    return torch.from_numpy(mask).to(_ingest_device(device)) == 0
+
+
+def load_kitti_batch(paths: List[str], device: Any = None, load_valid: bool = True):
+    """B200-native batched form of :func:`load_kitti`: N KITTI flow pngs of one size -> flow (N,2,H,W) fp32 and the
+    valid mask (N,H,W) bool on `device`.  The png inflate is host work (cv2, as in the reference); the uint16
+    payloads go up in one copy and the channel flip, the ``(u16 - 2**15) / 64`` conversion and the valid test run in
+    one kernel (``ofb_kitti_decode``)."""
+    import cv2
+    if not isinstance(paths, (list, tuple)) or len(paths) == 0:
+        raise TypeError("Error loading flow from KITTI data: Paths needs to be a non-empty list of strings")
+    decoded = []
+    for p in paths:
+        inp = cv2.imread(p, cv2.IMREAD_UNCHANGED) if isinstance(p, str) else None
+        if inp is None:
+            raise ValueError("Error loading flow from KITTI data: Flow data could not be loaded")
+        if inp.ndim != 3 or inp.shape[-1] != 3 or inp.dtype != np.uint16:
+            raise ValueError("Error loading flow from KITTI data: Loaded flow data has the wrong shape")
+        if inp.shape != decoded[0].shape if decoded else False:
+            raise ValueError("Error loading flow from KITTI data: All files of a batch need to have the same size")
+        decoded.append(inp)
+    device = _ingest_device(device)
+    staging = torch.empty((len(paths),) + decoded[0].shape, dtype=torch.int16).pin_memory()
+    for i, inp in enumerate(decoded):
+        staging[i].numpy().view(np.uint16)[...] = inp
+    flow, valid = _ops.kitti_decode(staging.to(device, non_blocking=True), load_valid)
+    return (flow, valid) if load_valid else (flow, None)
+
+
+def load_kitti(path: str, device: Any = None) -> torch.Tensor:
+    """(3,H,W) fp32 tensor: flow x, flow y, valid (0/1) from a KITTI uint16 ``.png`` (reference utils.py:811-829)."""
+    flow, valid = load_kitti_batch([path], device, True)
+    return torch.cat((flow[0], valid[0].to(torch.float32).unsqueeze(0)), dim=0)
+
+
+def _valid_scale(scale) -> list:
+    """reference utils.py:893-903"""
+    if isinstance(scale, (float, int)):
+        scale = [scale, scale]
+    elif isinstance(scale, (tuple, list)):
+        if len(scale) != 2:
+            raise ValueError("Error resizing flow: Scale {} must have a length of 2".format(type(scale)))
+        if not all(isinstance(item, (float, int)) for item in scale):
+            raise ValueError("Error resizing flow: Scale {} items must be integers or floats".format(type(scale)))
+    else:
+        raise TypeError("Error resizing flow: "
+                        "Scale must be an integer, float, or list or tuple of integers or floats")
+    if any(s <= 0 for s in scale):
+        raise ValueError("Error resizing flow: Scale values must be larger than 0")
+    return [float(scale[0]), float(scale[1])]
+
+
+def resize_flow(flow: Union[np.ndarray, torch.Tensor], scale: Union[float, int, list, tuple]) -> torch.Tensor:
+    """Bilinear resize of a flow field with the vectors rescaled accordingly; differentiable with respect to the
+    input flow.  Same arguments, errors and results as the reference (utils.py:878-916): `scale` is a number or
+    ``[vertical, horizontal]``; the output has ``floor(H * sv) x floor(W * sh)`` pixels."""
+    valid_flow = get_valid_vecs(flow, error_string="Error resizing flow: ")
+    scale = _valid_scale(scale)
+    resized = _ops.resize_flow(valid_flow, scale[0], scale[1])
+    if len(flow.shape) == 3:
+        resized = resized.squeeze(0)
+    return resized

@@ -513,3 +513,114 @@ def raw_warp_t_bwd(flow, target, gout, sign=1.0):
     gflow, gtgt = torch.empty_like(f), torch.empty_like(t)
     lib().orc_warp_t_bwd(_p(f), sign, _p(t), _p(g), _p(gflow), _p(gtgt), n, c, h, w)
     return gflow, gtgt
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# callers and data formats either side of the path: padding, resize, ingest
+# ----------------------------------------------------------------------------------------------------------------------
+def get_padding(fl: "OFlow"):
+    """reference flow_class.py:1174-1224, one item at a time like the reference (fp32 tensor ops, then ceil)."""
+    v = fl.vecs.clone()
+    v[(fl.vecs < 1e-3) & (fl.vecs > -1e-3)] = 0                       # threshold_vectors, utils.py:642
+    if fl.ref == 's':
+        v = v * -1
+    n, _, h, w = v.shape
+    gy, gx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
+    v[:, 0] -= gx
+    v[:, 1] -= gy
+    v *= -1
+    out = []
+    for i in range(n):
+        m = fl.mask[i]
+        pad = [max(-torch.min(v[i, 1, m]), 0), max(torch.max(v[i, 1, m]) - (h - 1), 0),
+               max(-torch.min(v[i, 0, m]), 0), max(torch.max(v[i, 0, m]) - (w - 1), 0)]
+        out.append([int(np.ceil(float(p))) for p in pad])
+    return out
+
+
+def _fma32(a, b, c):
+    """fp32 fused multiply-add emulated in fp64 (the product of two fp32 numbers is exact in fp64)."""
+    return (np.asarray(a, np.float32).astype(np.float64) * np.asarray(b, np.float32).astype(np.float64) +
+            np.asarray(c, np.float32).astype(np.float64)).astype(np.float32)
+
+
+def _resize_geom(n_out: int, scale: float, n_in: int):
+    """ATen upsample_bilinear2d, align_corners=False, scale factor given: src = fma(rs, dst + 0.5, -0.5) clamped at
+    0 with rs = float(1 / scale) (UpSample.h area_pixel_compute_source_index / guard_index_and_lambda; the FMA is the
+    CPU build's contraction, pinned by bit comparison against torch in tests/golden/make_ingest.py)."""
+    f32 = np.float32
+    d = np.arange(n_out, dtype=f32)
+    src = np.maximum(_fma32(f32(1.0 / scale), d + f32(0.5), f32(-0.5)), f32(0)).astype(f32)
+    i0 = np.minimum(src.astype(np.int64), n_in - 1)
+    i1 = i0 + (i0 < n_in - 1)
+    l1 = np.clip((src - i0.astype(f32)).astype(f32), f32(0), f32(1)).astype(f32)
+    return i0, i1, (f32(1) - l1).astype(f32), l1
+
+
+def resize_bilinear(a: np.ndarray, sy: float, sx: float) -> np.ndarray:
+    """(N,C,H,W) fp32 -> (N,C,floor(H*sy),floor(W*sx)) as
+    torch.nn.functional.interpolate(a, scale_factor=[sy, sx], mode='bilinear', align_corners=False) computes it on
+    CPU: bit-identical in the vectorised body of ATen's kernel, within an ulp or two in its scalar tail (which
+    contracts differently); the rounded masks of Flow.resize are bit-identical in every pinned case."""
+    a = np.asarray(a, np.float32)
+    h, w = a.shape[-2:]
+    ho, wo = int(np.floor(h * sy)), int(np.floor(w * sx))
+    y0, y1, h0, h1 = _resize_geom(ho, sy, h)
+    x0, x1, w0, w1 = _resize_geom(wo, sx, w)
+    top = _fma32(w0, a[:, :, y0][:, :, :, x0], (w1 * a[:, :, y0][:, :, :, x1]).astype(np.float32))
+    bot = _fma32(w0, a[:, :, y1][:, :, :, x0], (w1 * a[:, :, y1][:, :, :, x1]).astype(np.float32))
+    return _fma32(h0[:, None], top, (h1[:, None] * bot).astype(np.float32))
+
+
+def resize_flow(flow: torch.Tensor, scale) -> torch.Tensor:
+    """reference utils.py:878-916 (forward values)"""
+    s = [scale, scale] if isinstance(scale, (int, float)) else list(scale)
+    three = flow.dim() == 3
+    v = flow.unsqueeze(0) if three else flow
+    r = resize_bilinear(v.detach().numpy(), float(s[0]), float(s[1]))
+    r[:, 0] *= np.float32(s[1])
+    r[:, 1] *= np.float32(s[0])
+    r = torch.from_numpy(r)
+    return r.squeeze(0) if three else r
+
+
+def resize_flow_bwd(gout: torch.Tensor, scale, h: int, w: int) -> torch.Tensor:
+    """adjoint of resize_flow with respect to the (N,2,h,w) input flow"""
+    s = [scale, scale] if isinstance(scale, (int, float)) else list(scale)
+    g = gout.detach().numpy().astype(np.float64).copy()
+    g[:, 0] *= np.float32(s[1])
+    g[:, 1] *= np.float32(s[0])
+    n, c, ho, wo = g.shape
+    y0, y1, h0, h1 = _resize_geom(ho, float(s[0]), h)
+    x0, x1, w0, w1 = _resize_geom(wo, float(s[1]), w)
+    gin = np.zeros((n, c, h, w), np.float64)
+    for ys, wy in ((y0, h0), (y1, h1)):
+        for xs, wx in ((x0, w0), (x1, w1)):
+            wgt = wy[:, None].astype(np.float64) * wx[None, :].astype(np.float64)
+            np.add.at(gin, (slice(None), slice(None), ys[:, None], xs[None, :]), g * wgt)
+    return torch.from_numpy(gin.astype(np.float32))
+
+
+def resize_mask(mask: torch.Tensor, scale) -> torch.Tensor:
+    """reference flow_class.py:707-712: round(bilinear(mask.float())), torch.round = half to even"""
+    s = [scale, scale] if isinstance(scale, (int, float)) else list(scale)
+    r = resize_bilinear(mask.to(torch.float32).unsqueeze(1).numpy(), float(s[0]), float(s[1]))
+    return torch.from_numpy(np.rint(r)[:, 0] != 0)
+
+
+def load_sintel(path: str) -> torch.Tensor:
+    """reference utils.py:832-855"""
+    with open(path, 'rb') as fh:
+        if fh.read(4) != b'PIEH':
+            raise ValueError("not a .flo file")
+        w, h = int.from_bytes(fh.read(4), 'little'), int.from_bytes(fh.read(4), 'little')
+        flow = np.frombuffer(fh.read(), dtype='<f4').reshape(h, w, 2)
+    return torch.from_numpy(np.ascontiguousarray(np.moveaxis(flow, -1, 0)).astype(np.float32))
+
+
+def decode_kitti(png_bgr: np.ndarray) -> torch.Tensor:
+    """reference utils.py:824-829 applied to the decoded (H,W,3) uint16 array (cv2 channel order)"""
+    inp = png_bgr[..., ::-1].astype('float64')
+    inp[..., :2] = (inp[..., :2] - 2 ** 15) / 64
+    inp[inp[..., 2] > 0, 2] = 1
+    return torch.from_numpy(np.ascontiguousarray(np.moveaxis(inp, -1, 0)).astype(np.float32))
