@@ -6,14 +6,23 @@
 
 namespace ofb {
 
-__device__ __forceinline__ int classify(float v, bool m)
-{
-    int f = 0;
-    if (!isfinite(v)) f |= OFB_STAT_NONFINITE;
-    if (v != 0.0f) f |= OFB_STAT_NONZERO | (m ? OFB_STAT_NONZERO_M : 0);
-    if (!((v < OFB_THRESHOLD) && (v > -OFB_THRESHOLD))) f |= OFB_STAT_NONZERO_T | (m ? OFB_STAT_NONZERO_TM : 0);
-    return f;
-}
+// Every question reduces to the LARGEST |component| as an unsigned bit pattern (IEEE order = integer order for
+// non-negative floats, NaN/Inf patterns sort above every finite number):
+//   non-finite  <=>  max >= 0x7f800000        != 0  <=>  max != 0        |v| >= 1e-3 or NaN  <=>  max >= bits(1e-3f)
+// so the per-element work is one AND and one unsigned max (plus a multiply by the 0/1 mask byte, which runs on the
+// FMA pipe, and a second max for the masked variant).  The first version classified each element with five compares
+// and was bound by the ALU pipe (ncu: 90 % ALU, half the read bandwidth inside a step).
+struct AbsMax {
+    unsigned all, masked;
+    __device__ __forceinline__ void add(float v, unsigned m)
+    {
+        const unsigned u = __float_as_uint(v) & 0x7fffffffu;
+        all = max(all, u);
+        masked = max(masked, u * m);
+    }
+};
+
+constexpr int kStatsIters = 8;
 
 template <int VEC>
 __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict__ flow,
@@ -23,23 +32,46 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict
     const int n = blockIdx.y;
     const float *f = flow + (int64_t)n * 2 * HW;
     const uint8_t *m = mask ? mask + (int64_t)n * HW : nullptr;
-    int acc = 0;
-    const int stride = gridDim.x * blockDim.x * VEC;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < HW; i += stride) {
+    AbsMax am{0u, 0u};
+    // a CTA owns one contiguous chunk of kStatsIters * 256 * VEC pixels
+    const int base = blockIdx.x * (kStatsIters * 256 * VEC) + threadIdx.x * VEC;
+#pragma unroll 4
+    for (int k = 0; k < kStatsIters; ++k) {
+        const int i = base + k * (256 * VEC);
+        if (i >= HW) break;
         if constexpr (VEC == 4) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(f + i));
             const float4 b = __ldg(reinterpret_cast<const float4 *>(f + HW + i));
             uchar4 mm = make_uchar4(1, 1, 1, 1);
             if (m) mm = __ldg(reinterpret_cast<const uchar4 *>(m + i));
-            acc |= classify(a.x, mm.x) | classify(a.y, mm.y) | classify(a.z, mm.z) | classify(a.w, mm.w);
-            acc |= classify(b.x, mm.x) | classify(b.y, mm.y) | classify(b.z, mm.z) | classify(b.w, mm.w);
+            const unsigned m0 = mm.x != 0, m1 = mm.y != 0, m2 = mm.z != 0, m3 = mm.w != 0;
+            am.add(a.x, m0); am.add(a.y, m1); am.add(a.z, m2); am.add(a.w, m3);
+            am.add(b.x, m0); am.add(b.y, m1); am.add(b.z, m2); am.add(b.w, m3);
         } else {
-            const bool mm = m ? (__ldg(m + i) != 0) : true;
-            acc |= classify(__ldg(f + i), mm) | classify(__ldg(f + HW + i), mm);
+            const unsigned mm = m ? (__ldg(m + i) != 0) : 1u;
+            am.add(__ldg(f + i), mm);
+            am.add(__ldg(f + HW + i), mm);
         }
     }
-    acc = __reduce_or_sync(0xffffffffu, acc);
-    if ((threadIdx.x & 31) == 0 && acc != 0) atomicOr(flags + n, acc);
+    // one flag update per CTA, and none once the item's flags already hold these bits: 2000 warps OR-ing into the
+    // same word serialise in one L2 slice and doubled the kernel time (tools/readbench.cu vs the first version)
+    __shared__ unsigned s_all[8], s_masked[8];
+    unsigned all = __reduce_max_sync(0xffffffffu, am.all), masked = __reduce_max_sync(0xffffffffu, am.masked);
+    if ((threadIdx.x & 31) == 0) { s_all[threadIdx.x >> 5] = all; s_masked[threadIdx.x >> 5] = masked; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        all = __reduce_max_sync(0xffffffffu, threadIdx.x < 8 ? s_all[threadIdx.x] : 0u);
+        masked = __reduce_max_sync(0xffffffffu, threadIdx.x < 8 ? s_masked[threadIdx.x] : 0u);
+        if (threadIdx.x == 0 && all != 0) {
+            const unsigned thr = __float_as_uint(OFB_THRESHOLD);
+            int fl = OFB_STAT_NONZERO;
+            if (all >= 0x7f800000u) fl |= OFB_STAT_NONFINITE;
+            if (all >= thr) fl |= OFB_STAT_NONZERO_T;
+            if (masked != 0) fl |= OFB_STAT_NONZERO_M;
+            if (masked >= thr) fl |= OFB_STAT_NONZERO_TM;
+            if ((*reinterpret_cast<volatile int32_t *>(flags + n) & fl) != fl) atomicOr(flags + n, fl);
+        }
+    }
 }
 
 // self-test: the coordinate round trip with the constant-reciprocal division must equal the one with the IEEE
@@ -81,7 +113,7 @@ extern "C" int ofb_flow_stats(const float *flow, const uint8_t *mask, int32_t *f
     const int HW = H * W;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool vec4 = (HW % 4 == 0) && aligned16(flow) && (reinterpret_cast<uintptr_t>(mask) % 4 == 0);
-    const int per_block = 256 * (vec4 ? 4 : 1) * 8;   // 8 iterations per thread
+    const int per_block = 256 * (vec4 ? 4 : 1) * kStatsIters;
     int gx = (HW + per_block - 1) / per_block;
     if (gx < 1) gx = 1;
     const dim3 grid(gx, N);

@@ -1,5 +1,6 @@
-"""A/B timing of the W forward/adjoint kernels of two builds of the library on the same box (tuning aid).
-usage: python tools/ab_fwd.py <old.so>   (the old build must export the same ABI subset used by the 't' warp)"""
+"""A/B timing of the W forward/adjoint kernels of several builds of the library on the same box (tuning aid).
+usage: python tools/ab_fwd.py [name=]lib.so ...   (each build must export the ABI subset used by the 't' warp; the
+current build is measured as "new")"""
 import os, subprocess, sys
 code = r'''
 import sys, torch
@@ -20,9 +21,10 @@ def run(steps=8):
     return {k: round(sum(v) / len(v), 4) for k, v in per.items()}
 print(run())
 '''
-old = os.path.abspath(sys.argv[1])
+libs = [(a.split("=", 1) if "=" in a else ("old", a)) for a in sys.argv[1:]]
+libs = [(n, os.path.abspath(l)) for n, l in libs] + [("new", "")]
 for rep in range(2):
-    for name, lib in (("old", old), ("new", "")):
+    for name, lib in libs:
         env = dict(os.environ)
         env["OFB_SKIP_ABI_TABLE"] = "1"
         if lib:
