@@ -583,41 +583,68 @@ __global__ void __launch_bounds__(256) splat_bwd_kernel(const SplatBwdParams p, 
 // The v0 gather evaluates gnum_c = g'_c/dc and gden at every tap: 2C+3 scalar gathers per tap, 4 taps per source.
 // Here a prepass writes G[p] = {gnum_0 .. gnum_{C-1}, gden} once per TARGET pixel, interleaved (KG = 2/4/8 floats),
 // and the per-source kernel fetches each tap with one 64/128-bit load.  
+constexpr int kPreRows = 4;        // rows per thread; CTA tile = 64 x 16 (2 warps across x, 4 across y)
+
 template <int C, int KG>
 __global__ void __launch_bounds__(256) splat_bwd_prepass_kernel(const SplatBwdParams p, float *__restrict__ G)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * (4 * kPreRows) + (warp >> 1) * kPreRows;
     const int n = blockIdx.z;
-    if (x >= p.W || y >= p.H) return;
+    if (x >= p.W || y0 >= p.H) return;
+    const int rows = min(kPreRows, p.H - y0);
     const int HW = p.H * p.W;
-    const int pix = y * p.W + x;
-    const float dq = __ldg(p.density + (int64_t)n * HW + pix);
-    const float dc = fmaxf(dq, OFB_MIN_DENSITY);
-    const bool dead = p.unocc && (__ldg(p.unocc + (int64_t)n * HW + pix) != 0);     // utils.py:1203 overwrote it
-    float v[KG];
+    const float *den = p.density + (int64_t)n * HW;
+    const uint8_t *uno = p.unocc ? p.unocc + (int64_t)n * HW : nullptr;
+    const float *go = p.gout + (int64_t)n * C * HW, *ou = p.out + (int64_t)n * C * HW;
+    const float *gd = p.gdensity ? p.gdensity + (int64_t)n * HW : nullptr;
+    float *gp = G + (int64_t)n * HW * KG;
+    asm volatile("" : "+l"(den), "+l"(uno), "+l"(go), "+l"(ou), "+l"(gd), "+l"(gp));
+
+    // all loads of the column first (a streaming kernel lives on bytes in flight), arithmetic after
+    float dq[kPreRows], g[kPreRows][C > 0 ? C : 1], o[kPreRows][C > 0 ? C : 1], gden[kPreRows];
+    bool dead[kPreRows];
 #pragma unroll
-    for (int j = 0; j < KG; ++j) v[j] = 0.0f;
-    float s = 0.0f;
-    if (!dead) {
-        const float *go = p.gout + (int64_t)n * C * HW + pix, *ou = p.out + (int64_t)n * C * HW + pix;
+    for (int r = 0; r < kPreRows; ++r) {
+        if (r >= rows) break;
+        const int pix = (y0 + r) * p.W + x;
+        dq[r] = __ldg(den + pix);
+        dead[r] = uno && (__ldg(uno + pix) != 0);                   // utils.py:1203 overwrote it
+        gden[r] = gd ? __ldg(gd + pix) : 0.0f;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float g = __ldg(go + c * HW);
-            v[c] = g / dc;
-            s += g * __ldg(ou + c * HW);
+            g[r][c] = __ldg(go + (c * HW + pix));
+            o[r][c] = __ldg(ou + (c * HW + pix));
         }
     }
-    float gden = p.gdensity ? __ldg(p.gdensity + (int64_t)n * HW + pix) : 0.0f;
-    if (!dead && dq >= OFB_MIN_DENSITY) gden -= s / dc;            // clamp_min passes the gradient where den >= 1e-3
-    v[C] = gden;
-    float *gp = G + ((int64_t)n * HW + pix) * KG;
-    if constexpr (KG == 2) {
-        *reinterpret_cast<float2 *>(gp) = make_float2(v[0], v[1]);
-    } else {
 #pragma unroll
-        for (int h = 0; h < KG / 4; ++h)
-            reinterpret_cast<float4 *>(gp)[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+    for (int r = 0; r < kPreRows; ++r) {
+        if (r >= rows) break;
+        const int pix = (y0 + r) * p.W + x;
+        const float dc = fmaxf(dq[r], OFB_MIN_DENSITY);
+        float v[KG];
+#pragma unroll
+        for (int j = 0; j < KG; ++j) v[j] = 0.0f;
+        float s = 0.0f;
+        if (!dead[r]) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                v[c] = g[r][c] / dc;
+                s += g[r][c] * o[r][c];
+            }
+        }
+        float gdn = gden[r];
+        if (!dead[r] && dq[r] >= OFB_MIN_DENSITY) gdn -= s / dc;    // clamp_min passes the gradient where den >= 1e-3
+        v[C] = gdn;
+        float *gq = gp + (int64_t)pix * KG;
+        if constexpr (KG == 2) {
+            *reinterpret_cast<float2 *>(gq) = make_float2(v[0], v[1]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < KG / 4; ++h)
+                reinterpret_cast<float4 *>(gq)[h] = make_float4(v[4 * h], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+        }
     }
 }
 
@@ -869,7 +896,7 @@ extern "C" int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_b
     const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
     SplatBwdV1 k;
     if (work && splat_bwd_v1(C, &k) && work_floats >= (int64_t)N * H * W * k.kg) {
-        k.pre<<<grid, block, 0, st>>>(p, work);
+        k.pre<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
         OFB_CHECK_LAUNCH();
         k.gat<<<grid, block, 0, st>>>(p, work);
         OFB_CHECK_LAUNCH();
