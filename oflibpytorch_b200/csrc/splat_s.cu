@@ -667,82 +667,105 @@ __device__ __forceinline__ void load_g(const float *__restrict__ G, int q, float
 template <int C, int KG>
 __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdParams p, const float *__restrict__ G)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * (4 * kPreRows) + (warp >> 1) * kPreRows;
     const int n = blockIdx.z;
-    if (x >= p.W || y >= p.H) return;
+    if (x >= p.W || y0 >= p.H) return;
+    const int rows = min(kPreRows, p.H - y0);
     const int HW = p.H * p.W;
-    const int pix = y * p.W + x;
-    const float fx = __ldg(p.cx + (int64_t)n * p.coord_bs + pix);
-    const float fy = __ldg(p.cy + (int64_t)n * p.coord_bs + pix);
-    float X = fx, Y = fy;
-    bool fm = true;
-    if (p.relative) {
-        X = __fadd_rn(__fmul_rn(p.sign, fx), (float)x);
-        Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)y);
-        if (p.occlude_zero) fm = !is_zero_vec(fx, fy);
-    }
-    if (p.flow_mask) fm = fm && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix) != 0);
+    const float *cx = p.cx + (int64_t)n * p.coord_bs, *cy = p.cy + (int64_t)n * p.coord_bs;
+    const uint8_t *fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
+    const float *data = p.data + (int64_t)n * p.data_bs;
+    const float *Gn = G + (int64_t)n * HW * KG;
+    const uint8_t *uno = (p.gdata && p.unocc) ? p.unocc + (int64_t)n * HW : nullptr;
+    const float *go = p.gout + (int64_t)n * C * HW;
+    float *gdp = p.gdata ? p.gdata + (int64_t)n * C * HW : nullptr;
+    float *gcx = p.gcx ? p.gcx + (int64_t)n * p.gcoord_bs : nullptr, *gcy = p.gcx ? p.gcy + (int64_t)n * p.gcoord_bs : nullptr;
+    asm volatile("" : "+l"(cx), "+l"(cy), "+l"(fmask), "+l"(data), "+l"(Gn), "+l"(uno), "+l"(go), "+l"(gdp), "+l"(gcx), "+l"(gcy));
 
-    float gd[C], gx = 0.0f, gy = 0.0f;
+    // the streamed inputs of the whole column first, then the dependent tap gathers row by row
+    float fxs[kPreRows], fys[kPreRows], dats[kPreRows][C];
+    uint8_t fms[kPreRows], uns[kPreRows];
 #pragma unroll
-    for (int c = 0; c < C; ++c) gd[c] = 0.0f;
-    if (fm) {
-        const float *data = p.data + (int64_t)n * p.data_bs + pix;
-        float dat[C];
+    for (int r = 0; r < kPreRows; ++r) {
+        if (r >= rows) break;
+        const int pix = (y0 + r) * p.W + x;
+        fxs[r] = __ldg(cx + pix);
+        fys[r] = __ldg(cy + pix);
+        fms[r] = fmask ? __ldg(fmask + pix) : 1;
+        uns[r] = uno ? __ldg(uno + pix) : 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) dat[c] = __ldg(data + c * HW);
-        const float x0f = floorf(X), y0f = floorf(Y);
-        const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
-        const bool bx[2] = {(unsigned)xi < (unsigned)p.W, (unsigned)(xi + 1) < (unsigned)p.W};
-        const bool by[2] = {(unsigned)yi < (unsigned)p.H, (unsigned)(yi + 1) < (unsigned)p.H};
-        const float ax[2] = {__fsub_rn(__fadd_rn(x0f, 1.0f), X), __fsub_rn(X, x0f)};
-        const float ay[2] = {__fsub_rn(__fadd_rn(y0f, 1.0f), Y), __fsub_rn(Y, y0f)};
-        const float wx[2] = {bx[0] ? ax[0] : 0.0f, bx[1] ? ax[1] : 0.0f};      // utils.py:1110
-        const float wy[2] = {by[0] ? ay[0] : 0.0f, by[1] ? ay[1] : 0.0f};      // utils.py:1111
-        const float *Gn = G + (int64_t)n * HW * KG;
-        const int o = yi * p.W + xi;
-        float Gv[2][2];
+        for (int c = 0; c < C; ++c) dats[r][c] = __ldg(data + (c * HW + pix));
+    }
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                Gv[a][b] = 0.0f;
-                if (!(bx[b] && by[a])) continue;                            // contributes to nothing
-                float g[KG];
-                load_g<KG>(Gn, o + a * p.W + b, g);
-                const float w = __fmul_rn(wy[a], wx[b]);
-                float acc = g[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    acc = __fmaf_rn(g[c], dat[c], acc);
-                    gd[c] = __fmaf_rn(w, g[c], gd[c]);
-                }
-                Gv[a][b] = acc;
-            }
-        const float ibx0 = bx[0] ? 1.0f : 0.0f, ibx1 = bx[1] ? 1.0f : 0.0f;
-        const float iby0 = by[0] ? 1.0f : 0.0f, iby1 = by[1] ? 1.0f : 0.0f;
-        // d w / d x: wx[0] = (x1 - x)*inbx[0] -> -inbx[0];  wx[1] = (x - x0)*inbx[1] -> +inbx[1]
-        gx = wy[0] * (ibx1 * Gv[0][1] - ibx0 * Gv[0][0]) + wy[1] * (ibx1 * Gv[1][1] - ibx0 * Gv[1][0]);
-        gy = wx[0] * (iby1 * Gv[1][0] - iby0 * Gv[0][0]) + wx[1] * (iby1 * Gv[1][1] - iby0 * Gv[0][1]);
+    for (int r = 0; r < kPreRows; ++r) {
+        if (r >= rows) break;
+        const int y = y0 + r, pix = y * p.W + x;
+        const float fx = fxs[r], fy = fys[r];
+        float X = fx, Y = fy;
+        bool fm = true;
         if (p.relative) {
-            gx *= p.sign;
-            gy *= p.sign;
+            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)x);
+            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)y);
+            if (p.occlude_zero) fm = !is_zero_vec(fx, fy);
         }
-    }
-    if (p.gdata) {
-        const bool self_unocc = p.unocc && (__ldg(p.unocc + (int64_t)n * HW + pix) != 0);
-        float *gdp = p.gdata + (int64_t)n * C * HW + pix;
+        fm = fm && (fms[r] != 0);
+
+        float gd[C], gx = 0.0f, gy = 0.0f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float v = gd[c];
-            if (self_unocc) v += __ldg(p.gout + ((int64_t)n * C + c) * HW + pix);
-            gdp[c * HW] = v;
+        for (int c = 0; c < C; ++c) gd[c] = 0.0f;
+        if (fm) {
+            const float *dat = dats[r];
+            const float x0f = floorf(X), y0f = floorf(Y);
+            const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
+            const bool bx[2] = {(unsigned)xi < (unsigned)p.W, (unsigned)(xi + 1) < (unsigned)p.W};
+            const bool by[2] = {(unsigned)yi < (unsigned)p.H, (unsigned)(yi + 1) < (unsigned)p.H};
+            const float ax[2] = {__fsub_rn(__fadd_rn(x0f, 1.0f), X), __fsub_rn(X, x0f)};
+            const float ay[2] = {__fsub_rn(__fadd_rn(y0f, 1.0f), Y), __fsub_rn(Y, y0f)};
+            const float wx[2] = {bx[0] ? ax[0] : 0.0f, bx[1] ? ax[1] : 0.0f};      // utils.py:1110
+            const float wy[2] = {by[0] ? ay[0] : 0.0f, by[1] ? ay[1] : 0.0f};      // utils.py:1111
+            const int o = yi * p.W + xi;
+            float Gv[2][2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    Gv[a][b] = 0.0f;
+                    if (!(bx[b] && by[a])) continue;                            // contributes to nothing
+                    float g[KG];
+                    load_g<KG>(Gn, o + a * p.W + b, g);
+                    const float w = __fmul_rn(wy[a], wx[b]);
+                    float acc = g[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        acc = __fmaf_rn(g[c], dat[c], acc);
+                        gd[c] = __fmaf_rn(w, g[c], gd[c]);
+                    }
+                    Gv[a][b] = acc;
+                }
+            const float ibx0 = bx[0] ? 1.0f : 0.0f, ibx1 = bx[1] ? 1.0f : 0.0f;
+            const float iby0 = by[0] ? 1.0f : 0.0f, iby1 = by[1] ? 1.0f : 0.0f;
+            // d w / d x: wx[0] = (x1 - x)*inbx[0] -> -inbx[0];  wx[1] = (x - x0)*inbx[1] -> +inbx[1]
+            gx = wy[0] * (ibx1 * Gv[0][1] - ibx0 * Gv[0][0]) + wy[1] * (ibx1 * Gv[1][1] - ibx0 * Gv[1][0]);
+            gy = wx[0] * (iby1 * Gv[1][0] - iby0 * Gv[0][0]) + wx[1] * (iby1 * Gv[1][1] - iby0 * Gv[0][1]);
+            if (p.relative) {
+                gx *= p.sign;
+                gy *= p.sign;
+            }
         }
-    }
-    if (p.gcx) {
-        p.gcx[(int64_t)n * p.gcoord_bs + pix] = gx;
-        p.gcy[(int64_t)n * p.gcoord_bs + pix] = gy;
+        if (gdp) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float v = gd[c];
+                if (uns[r]) v += __ldg(go + (c * HW + pix));
+                gdp[c * HW + pix] = v;
+            }
+        }
+        if (gcx) {
+            gcx[pix] = gx;
+            gcy[pix] = gy;
+        }
     }
 }
 
@@ -898,7 +921,7 @@ extern "C" int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_b
     if (work && splat_bwd_v1(C, &k) && work_floats >= (int64_t)N * H * W * k.kg) {
         k.pre<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
         OFB_CHECK_LAUNCH();
-        k.gat<<<grid, block, 0, st>>>(p, work);
+        k.gat<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
         OFB_CHECK_LAUNCH();
         return 0;
     }
