@@ -243,3 +243,35 @@ def test_chained_combine_apply_backward_matches_oracle():
         assert_mask_equal(val_g[i], val_o[i], 'valid %d' % i)
         assert_grad_close(gf_g[i], gf_o[i], 'gflow %d' % i)
     assert_grad_close(gi_g, gi_o, 'gimg')
+
+
+@pytest.mark.parametrize('ref', ['t', 's'])
+def test_run_to_run_determinism(ref):
+    """Masks and every W output are bit-identical from run to run.  The splat and both adjoints accumulate with
+    floating-point atomics whose order is not fixed: their floats may differ in the last bits (bounded here at 1e-5
+    of the tensor's scale), their masks never do -- validity is decided by order-independent tests."""
+    n, h, w = 2, 211, 333
+    flow = smooth_flow(n, h, w, 9.0, 71).cuda()
+    img = torch.rand(n, 3, h, w, generator=gen(72)).cuda()
+    fmask, tmask = holed_mask(n, h, w, 73).cuda(), holed_mask(n, h, w, 74).cuda()
+    gout = torch.rand(n, 3, h, w, generator=gen(75)).cuda()
+
+    def run():
+        f, i = flow.clone().requires_grad_(), img.clone().requires_grad_()
+        fl = of().Flow(f, ref, fmask)
+        out, valid = fl.apply(i, tmask, return_valid_area=True)
+        out.backward(gout)
+        sw = fl.switch_ref()
+        return out.detach(), valid, f.grad, i.grad, sw.vecs.detach(), sw.mask, fl.valid_source(), fl.valid_target()
+
+    first = run()
+    for _ in range(3):
+        again = run()
+        for k, (a, b) in enumerate(zip(first, again)):
+            if a.dtype == torch.bool:
+                assert torch.equal(a, b), 'mask output %d changed between runs' % k
+            elif ref == 't' and k == 0:
+                assert torch.equal(a, b), 'the W forward is a pure gather and must be bit-identical'
+            else:
+                scale = float(a.abs().max()) + 1e-12
+                assert float((a - b).abs().max()) <= 1e-5 * scale, 'output %d drifted between runs' % k
