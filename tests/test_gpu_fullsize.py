@@ -1,0 +1,117 @@
+"""Parity at BASELINE.json's FULL sizes (configs 2, 3 and 4).  The oracle cannot run 64 x 1080p in seconds, so the
+full-size results are checked through properties that do not depend on the size:
+
+* batch independence + sampling: every batch item is independent, so a few items of the full-batch
+  result are compared with the ORACLE run on just those items -- masks bit-exact, W forward bit-exact, floats and
+  gradients within the tolerance of BASELINE.json;
+* the adjoint identity <A x, g> = <x, A^T g> ties each hand-written backward kernel to its forward at full size;
+* linearity in the payload;
+* integer / half-pixel translations (the adversarial cases for the mask bits) give every item the oracle's mask.
+Inputs are the bench's own (bench.make_inputs: SURVEY 8d cfg 2) or the same recipe at the other configs' sizes."""
+import os
+import sys
+
+import pytest
+import torch
+
+from helpers import assert_close, assert_grad_close, assert_mask_equal
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+pytestmark = pytest.mark.gpu
+
+SAMPLES = (0, 37, 63)
+
+
+def of():
+    import oflibpytorch_b200
+    return oflibpytorch_b200
+
+
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def dot(a, b):
+    return float((a.double() * b.double()).sum())
+
+
+@pytest.mark.parametrize('ref,n', [('t', 64), ('s', 32)])
+def test_full_batch_items_match_the_oracle(ref, n):
+    """configs 2 ('t', 64 x 3 x 1080 x 1920) and 3 ('s', 32 x ...): Flow.apply + valid area, forward and backward"""
+    import bench
+    flow, img, mask, tmask, gout = bench.make_inputs(n, 'cuda')
+    if ref == 's':
+        flow[:, :, 200:440, 300:700] = 0.0                       # cfg 3: blocks of exactly-zero flow (occlusion rule)
+    f, i = flow.clone().requires_grad_(), img.clone().requires_grad_()
+    out, valid = of().Flow(f, ref, mask).apply(i, tmask, return_valid_area=True)
+    out.backward(gout)
+    # adjoint identity over the whole batch, payload side: <A img, gout> = <img, A^T gout> (A is linear in img)
+    lhs, rhs = dot(out.detach(), gout), dot(img, i.grad)
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs), (lhs, rhs)
+    for k in [s for s in SAMPLES if s < n]:
+        fo, io = flow[k:k + 1].cpu().requires_grad_(), img[k:k + 1].cpu().requires_grad_()
+        oo, vo = orc().OFlow(fo, ref, mask[k:k + 1].cpu()).apply(io, tmask[k:k + 1].cpu(), return_valid_area=True)
+        oo.backward(gout[k:k + 1].cpu())
+        assert_mask_equal(valid[k:k + 1], vo, 'valid[%d]' % k)
+        if ref == 't':
+            assert torch.equal(out[k:k + 1].detach().cpu(), oo.detach()), 'W forward is bit-identical to the oracle'
+        else:
+            assert_close(out[k:k + 1], oo, 'out[%d]' % k)
+        assert_grad_close(f.grad[k:k + 1], fo.grad, 'gflow[%d]' % k)
+        assert_grad_close(i.grad[k:k + 1], io.grad, 'gimg[%d]' % k)
+
+
+@pytest.mark.parametrize('ref', ['t', 's'])
+def test_full_size_linearity_in_the_payload(ref):
+    import bench
+    n = 32
+    flow, img, mask, tmask, gout = bench.make_inputs(n, 'cuda')
+    fl = of().Flow(flow, ref, mask)
+    with torch.no_grad():
+        a = fl.apply(img)
+        b = fl.apply(gout)
+        c = fl.apply(0.25 * img - 3.0 * gout)
+    assert_close(c, 0.25 * a - 3.0 * b, 'linearity', rtol=1e-4, atol=1e-4)
+
+
+def test_config4_combine_and_switch_ref_items_match_the_oracle():
+    """config 4: 16 x 2160 x 3840, combine_with mode 3 then switch_ref, masks bit-exact"""
+    import bench
+    n, h, w = 16, 2160, 3840
+    fa, fb = bench.smooth_flow(n, h, w, 8.0, 8, 'cuda'), bench.smooth_flow(n, h, w, 8.0, 9, 'cuda')
+    m = torch.ones(n, h, w, dtype=torch.bool, device='cuda')
+    m[:, 600:1000, 1400:2200] = False
+    m[:, :, ::97] = False
+    mb = m.roll(211, dims=2)
+    for ref in 'ts':
+        with torch.no_grad():
+            c3 = of().Flow(fa, ref, m).combine_with(of().Flow(fb, ref, mb), 3)
+            sw = c3.switch_ref()
+        k = 5
+        o = orc()
+        oc = o.OFlow(fa[k:k + 1].cpu(), ref, m[k:k + 1].cpu()).combine_with(
+            o.OFlow(fb[k:k + 1].cpu(), ref, mb[k:k + 1].cpu()), 3)
+        assert_mask_equal(c3.mask[k:k + 1], oc.mask, 'combine mask ' + ref)
+        assert_close(c3.vecs[k:k + 1], oc.vecs, 'combine vecs ' + ref)
+        # switch_ref of the CUDA result through the oracle: same input bits on both sides
+        osw = o.OFlow(c3.vecs[k:k + 1].cpu(), ref, c3.mask[k:k + 1].cpu()).switch_ref()
+        assert_mask_equal(sw.mask[k:k + 1], osw.mask, 'switch_ref mask ' + ref)
+        assert_close(sw.vecs[k:k + 1], osw.vecs, 'switch_ref vecs ' + ref)
+
+
+def test_full_size_integer_and_half_pixel_translations_match_the_oracle():
+    """flow = (7, -3) and (7.5, -2.5) everywhere on a full 1080p batch (SURVEY 8d adversarial cases (a), (b): sample
+    positions sit exactly on pixel centres / pixel edges, where the coordinate round trip decides the mask bit).  Every
+    item sees the same field, so each item of the batch must equal the oracle's single-item result bit for bit."""
+    n, h, w = 16, 1080, 1920
+    o = orc()
+    for vx, vy in ((7.0, -3.0), (7.5, -2.5)):
+        flow = torch.empty(n, 2, h, w, device='cuda')
+        flow[:, 0], flow[:, 1] = vx, vy
+        one = flow[:1].cpu()
+        for ref in 'ts':
+            fl, ofl = of().Flow(flow, ref), o.OFlow(one, ref)
+            assert_mask_equal(fl.valid_target(), ofl.valid_target().expand(n, h, w), 'valid_target ' + ref)
+            assert_mask_equal(fl.valid_source(), ofl.valid_source().expand(n, h, w), 'valid_source ' + ref)
