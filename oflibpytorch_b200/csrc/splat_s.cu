@@ -159,15 +159,17 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const SplatParams 
 }
 
 // ------------------------------------------------------------------------------------------------
-// v1 forward: interleaved accumulators, vector REDs, register merging, L2-resident per-item passes
+// v1 forward: interleaved accumulators, vector REDs, register merging
 // ------------------------------------------------------------------------------------------------
 // The accumulator is this library's private workspace, so its layout is free: KP = 4 or 8 floats PER TARGET PIXEL
 // ([num_0 .. num_{C-1}, den, bad, pad]) instead of C+2 planes.  Every tap site is then ONE
 // red.global.add.v4.f32 (SASS REDG.E.ADD.F32x4) instead of C+2 scalar REDs, and the normalise pass reads one
 // float4 per pixel.  Contributions are merged in registers before they reach the L2 exactly as in the W adjoint
 // (csrc/warp_t.cu): lane l's east taps are lane l+1's west taps when the endpoints chain, and a thread carries its
-// south taps into the next source row.  Items are processed one (or a few) at a time -- zero-fill, accumulate,
-// normalise back to back on one small workspace -- so the accumulator lives in the 126 MB L2 and never reaches HBM.
+// south taps into the next source row.  The whole batch goes through zero-fill, accumulate, normalise in three
+// launches (OFB_SPLAT_CHUNK_MB splits it): per-item passes meant to keep the accumulator in the L2 were measured
+// slower, with and without a persisting access-policy window, and so was a persistent kernel sweeping an L2-sized
+// ring of accumulator rows (profiles/r01_ring_splat_experiment.patch).
 constexpr int kSplatRows = 8;      // source rows per thread; CTA tile = 64 x 32 (2 warps across x, 4 across y)
 
 template <int KP> struct AccVec { float v[KP]; };
