@@ -249,6 +249,7 @@ class _WarpT(torch.autograd.Function):
         ctx.save_for_backward(flow, src)
         ctx.sign, ctx.add_flow = sign, add_flow
         ctx.mark_non_differentiable(valid)
+        ctx.set_materialize_grads(False)     # no zero-filled stand-in for the gradient of the boolean output
         return out, valid
 
     @staticmethod
@@ -257,7 +258,7 @@ class _WarpT(torch.autograd.Function):
         flow, src = ctx.saved_tensors
         need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gflow = gsrc = None
-        if need_gflow or need_gsrc:
+        if gout is not None and (need_gflow or need_gsrc):
             gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc)
             if need_gflow:
                 gflow = _reduce_to(gf, flow)
@@ -274,6 +275,7 @@ class _SplatS(torch.autograd.Function):
         ctx.save_for_backward(cx, cy, data, flow_mask, out, density, unocc)
         ctx.relative, ctx.sign, ctx.occlude_zero = relative, sign, occlude_zero
         ctx.mark_non_differentiable(wmask, valid)
+        ctx.set_materialize_grads(False)     # an unused density output must not cost a zero-filled gradient
         return out, density, wmask, valid
 
     @staticmethod
@@ -283,7 +285,7 @@ class _SplatS(torch.autograd.Function):
         need_gc = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_gd = ctx.needs_input_grad[2]
         gcx = gcy = gdata = None
-        if need_gc or need_gd:
+        if (gout is not None or gdensity is not None) and (need_gc or need_gd):
             gcoord, gd = _ops.splat_s_bwd(cx, cy, ctx.relative, ctx.sign, data, flow_mask, ctx.occlude_zero,
                                           out, density, unocc, gout, gdensity, need_gc, need_gd)
             if need_gc:
@@ -336,6 +338,7 @@ class _SplatFlow(torch.autograd.Function):
         ctx.save_for_backward(flow, data, flow_mask, out, density, unocc)
         ctx.sign, ctx.occlude_zero = sign, occlude_zero
         ctx.mark_non_differentiable(wmask, valid)
+        ctx.set_materialize_grads(False)
         return out, density, wmask, valid
 
     @staticmethod
@@ -344,7 +347,7 @@ class _SplatFlow(torch.autograd.Function):
         flow, data, flow_mask, out, density, unocc = ctx.saved_tensors
         need_gf, need_gd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gflow = gdata = None
-        if need_gf or need_gd:
+        if (gout is not None or gdensity is not None) and (need_gf or need_gd):
             gcoord, gd = _ops.splat_s_bwd(flow[:, 0], flow[:, 1], True, ctx.sign, data, flow_mask,
                                           ctx.occlude_zero, out, density, unocc, gout, gdensity, need_gf, need_gd)
             if need_gf:
@@ -414,6 +417,7 @@ class _WarpTWin(torch.autograd.Function):
         ctx.save_for_backward(flow, src)
         ctx.sign, ctx.window = sign, list(window)
         ctx.mark_non_differentiable(valid)
+        ctx.set_materialize_grads(False)
         return out, valid
 
     @staticmethod
@@ -422,7 +426,7 @@ class _WarpTWin(torch.autograd.Function):
         flow, src = ctx.saved_tensors
         need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gflow = gsrc = None
-        if need_gflow or need_gsrc:
+        if gout is not None and (need_gflow or need_gsrc):
             gf, gs = _ops.warp_t_win_bwd(flow, ctx.sign, src, gout, need_gflow, need_gsrc, ctx.window)
             gflow = _reduce_to(gf, flow) if need_gflow else None
             gsrc = gs if need_gsrc else None
