@@ -53,3 +53,24 @@ def test_product_never_imports_the_oracle():
                     if s.startswith(('import ', 'from ', '#include')):
                         assert 'oracle' not in s, '%s references the oracle: %s' % (fn, s)
                     assert 'liboracle' not in s and '/root/reference' not in s, '%s: %s' % (fn, s)
+
+
+def test_header_is_valid_c99_and_links_from_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (not only C++), and a plain C program must be able to
+    link the library and call an entry point that needs no GPU."""
+    import shutil
+    import subprocess
+    from oflibpytorch_b200 import _native
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        import pytest
+        pytest.skip('no gcc')
+    src = tmp_path / 'probe.c'
+    src.write_text('#include <stdio.h>\n#include "oflib_b200.h"\n'
+                   'int main(void) { printf("%d %s\\n", ofb_abi_version(), ofb_error_string(OFB_EINVAL)); return 0; }\n')
+    exe = tmp_path / 'probe'
+    libdir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe),
+                    '-L', libdir, '-l:liboflib_b200.so', '-Wl,-rpath,' + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith('1 ') and 'invalid' in out
