@@ -142,6 +142,21 @@ int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_bs, int rela
                     uint8_t *valid, int valid_mode,
                     int N, int C, int H, int W, void *stream);
 
+/* ofb_splat_s_fwd for a flow that is a WINDOW of a larger frame -- the padded 's' apply without the padding
+ * (Flow.apply(padding=..., cut=True), flow_class.py:905-918, where the reference pads the flow to the target's size,
+ * splats the whole frame and slices the window back out).  All tensors are the H x W window; window (host, 4 ints) =
+ * {y0, x0, frame_h, frame_w}.  End points are computed in the frame (y + y0 + sign*cy, x + x0 + sign*cx: the same
+ * floats as the reference's), tested against the frame, and dropped when they land outside the window.  Relative
+ * coordinates only; payloads of up to 6 channels (OFB_EINVAL otherwise: use the padded path). */
+int ofb_splat_s_win_fwd(const float *cx, const float *cy, int64_t coord_bs, float sign,
+                        const float *data, int64_t data_bs,
+                        const uint8_t *data_mask, int64_t data_mask_bs,
+                        const uint8_t *flow_mask, int64_t flow_mask_bs,
+                        int occlude_zero, float *acc, int64_t acc_floats,
+                        float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
+                        uint8_t *valid, int valid_mode,
+                        int N, int C, int H, int W, const int *window, void *stream);
+
 /* Adjoint of ofb_splat_s_fwd with respect to the coordinates (hence the flow) and the data.
  *   out, density, unocc   the forward results (out BEFORE any dtype rounding; unocc NULL = none)
  *   gout (N,C,H,W); gdensity (N,H,W) NULL = zero
@@ -156,6 +171,16 @@ int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_bs, int rela
                     float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
                     float *work, int64_t work_floats,
                     int N, int C, int H, int W, void *stream);
+
+/* Adjoint of ofb_splat_s_win_fwd; `work` (ofb_splat_s_bwd_workspace) is required, C <= 7. */
+int ofb_splat_s_win_bwd(const float *cx, const float *cy, int64_t coord_bs, float sign,
+                        const float *data, int64_t data_bs,
+                        const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
+                        const float *out, const float *density, const uint8_t *unocc,
+                        const float *gout, const float *gdensity,
+                        float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                        float *work, int64_t work_floats,
+                        int N, int C, int H, int W, const int *window, void *stream);
 
 /* Workspace (in floats) ofb_splat_s_bwd wants for its vector-gather path; 0 = none.  `work` may be NULL (then the
  * generic scalar-gather kernel runs). */

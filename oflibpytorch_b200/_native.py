@@ -34,6 +34,10 @@ SIGNATURES = {
     'ofb_splat_s_bwd': ([_P, _P, _L, _I, _F, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _L,
                          _I, _I, _I, _I, _P], _I),
     'ofb_splat_s_bwd_workspace': ([_I, _I, _I, _I], _L),
+    'ofb_splat_s_win_fwd': ([_P, _P, _L, _F, _P, _L, _P, _L, _P, _L, _I, _P, _L, _P, _P, _P, _P, _P, _I,
+                             _I, _I, _I, _I, _P, _P], _I),
+    'ofb_splat_s_win_bwd': ([_P, _P, _L, _F, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _L,
+                             _I, _I, _I, _I, _P, _P], _I),
     'ofb_splat_s_kp': ([_I, _I], _I),
     'ofb_splat_s_band_accumulate': ([_P, _P, _L, _I, _F, _P, _L, _P, _L, _P, _L, _I, _P, _I, _I, _I, _I, _P, _P], _I),
     'ofb_splat_s_band_normalise': ([_P, _P, _L, _I, _P, _L, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _P, _I,

@@ -26,11 +26,11 @@ _lib.define("warp_t_fwd(Tensor flow, float sign, Tensor? src, Tensor? src_mask, 
 _lib.define("warp_t_bwd(Tensor flow, float sign, Tensor src, Tensor gout, float add_flow, "
             "bool need_gflow, bool need_gsrc) -> (Tensor, Tensor)")
 _lib.define("splat_s_fwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor? data, Tensor? data_mask, "
-            "Tensor? flow_mask, bool occlude_zero, int valid_mode, bool want_aux) -> "
+            "Tensor? flow_mask, bool occlude_zero, int valid_mode, bool want_aux, int[] window) -> "
             "(Tensor, Tensor, Tensor, Tensor, Tensor)")
 _lib.define("splat_s_bwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor data, Tensor? flow_mask, "
             "bool occlude_zero, Tensor out, Tensor density, Tensor? unocc, Tensor? gout, Tensor? gdensity, "
-            "bool need_gcoord, bool need_gdata) -> (Tensor, Tensor)")
+            "bool need_gcoord, bool need_gdata, int[] window) -> (Tensor, Tensor)")
 
 
 # Optional per-call device timing (bench.py): when PROFILE is a list, every C-ABI call is bracketed by CUDA events
@@ -164,7 +164,7 @@ def _coord_planes(cx: torch.Tensor, cy: torch.Tensor):
     return cx, cy
 
 
-def _splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask, occlude_zero, valid_mode, want_aux):
+def _splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask, occlude_zero, valid_mode, want_aux, window):
     require_cuda(cx, "flow")
     cx, cy = _coord_planes(cx, cy)
     data = None if data is None else _f32c(data)
@@ -184,19 +184,27 @@ def _splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask, occlude_zer
         wmask = torch.empty((n, h, w) if want_aux else (0,), dtype=torch.bool, device=dev)
         unocc = torch.empty((n, h, w) if (occlude_zero and want_aux) else (0,), dtype=torch.bool, device=dev)
         valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
-        _call("ofb_splat_s_fwd", 
-            _p(cx), _p(cy), 0 if (cx.shape[0] == 1 and n > 1) else cx.stride(0), int(relative), sign,
-            _p(data) if c else None, _bs(data, n, c * hw),
-            _p(data_mask), _bs(data_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
-            int(occlude_zero), _p(acc), acc_floats, _p(out) if c else None, _p(density) if want_aux else None,
-            _p(wmask) if want_aux else None, _p(unocc) if (occlude_zero and want_aux) else None,
-            _p(valid) if want_valid else None, valid_mode,
-            n, c, h, w, _stream())
+        head = (_p(cx), _p(cy), 0 if (cx.shape[0] == 1 and n > 1) else cx.stride(0))
+        tail = (_p(data) if c else None, _bs(data, n, c * hw),
+                _p(data_mask), _bs(data_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
+                int(occlude_zero), _p(acc), acc_floats, _p(out) if c else None, _p(density) if want_aux else None,
+                _p(wmask) if want_aux else None, _p(unocc) if (occlude_zero and want_aux) else None,
+                _p(valid) if want_valid else None, valid_mode, n, c, h, w)
+        if len(window):      # (y0, x0, frame_h, frame_w): the tensors are a window of a larger frame
+            _call("ofb_splat_s_win_fwd", *head, sign, *tail, _win_arr4(window), _stream())
+        else:
+            _call("ofb_splat_s_fwd", *head, int(relative), sign, *tail, _stream())
     return out, density, wmask, unocc, valid
 
 
+def _win_arr4(window):
+    if len(window) != 4:
+        raise ValueError("window needs 4 integers (y0, x0, frame_h, frame_w)")
+    return (ctypes.c_int * 4)(*[int(v) for v in window])
+
+
 def _splat_s_bwd(cx, cy, relative, sign, data, flow_mask, occlude_zero, out, density, unocc, gout, gdensity,
-                 need_gcoord, need_gdata):
+                 need_gcoord, need_gdata, window):
     require_cuda(cx, "flow")
     cx, cy = _coord_planes(cx, cy)
     data, out, density = _f32c(data), _f32c(out), _f32c(density)
@@ -213,12 +221,15 @@ def _splat_s_bwd(cx, cy, relative, sign, data, flow_mask, occlude_zero, out, den
         work = torch.empty((work_floats,), dtype=torch.float32, device=dev) if work_floats else None
         gcx = ctypes.c_void_p(gcoord.data_ptr()) if need_gcoord else None
         gcy = ctypes.c_void_p(gcoord.data_ptr() + 4 * hw) if need_gcoord else None
-        _call("ofb_splat_s_bwd", 
-            _p(cx), _p(cy), 0 if (cx.shape[0] == 1 and n > 1) else cx.stride(0), int(relative), sign,
-            _p(data), _bs(data, n, c * hw), _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero),
-            _p(out), _p(density), _p(unocc) if (unocc is not None and unocc.numel()) else None,
-            _p(gout), _p(gdensity), gcx, gcy, 2 * hw, _p(gdata) if need_gdata else None,
-            _p(work), work_floats, n, c, h, w, _stream())
+        head = (_p(cx), _p(cy), 0 if (cx.shape[0] == 1 and n > 1) else cx.stride(0))
+        tail = (_p(data), _bs(data, n, c * hw), _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero),
+                _p(out), _p(density), _p(unocc) if (unocc is not None and unocc.numel()) else None,
+                _p(gout), _p(gdensity), gcx, gcy, 2 * hw, _p(gdata) if need_gdata else None,
+                _p(work), work_floats, n, c, h, w)
+        if len(window):
+            _call("ofb_splat_s_win_bwd", *head, sign, *tail, _win_arr4(window), _stream())
+        else:
+            _call("ofb_splat_s_bwd", *head, int(relative), sign, *tail, _stream())
     return gcoord, gdata
 
 
@@ -271,7 +282,7 @@ class _SplatS(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cx, cy, data, data_mask, flow_mask, relative, sign, occlude_zero, valid_mode):
         out, density, wmask, unocc, valid = _ops.splat_s_fwd(cx, cy, relative, sign, data, data_mask, flow_mask,
-                                                             occlude_zero, valid_mode, True)
+                                                             occlude_zero, valid_mode, True, [])
         ctx.save_for_backward(cx, cy, data, flow_mask, out, density, unocc)
         ctx.relative, ctx.sign, ctx.occlude_zero = relative, sign, occlude_zero
         ctx.mark_non_differentiable(wmask, valid)
@@ -287,7 +298,7 @@ class _SplatS(torch.autograd.Function):
         gcx = gcy = gdata = None
         if (gout is not None or gdensity is not None) and (need_gc or need_gd):
             gcoord, gd = _ops.splat_s_bwd(cx, cy, ctx.relative, ctx.sign, data, flow_mask, ctx.occlude_zero,
-                                          out, density, unocc, gout, gdensity, need_gc, need_gd)
+                                          out, density, unocc, gout, gdensity, need_gc, need_gd, [])
             if need_gc:
                 gcx = _reduce_to(gcoord[:, 0], cx)
                 gcy = _reduce_to(gcoord[:, 1], cy)
@@ -311,32 +322,40 @@ def warp_t(flow, src, src_mask=None, flow_mask=None, sign=1.0, add_flow=0.0, thr
 
 
 def splat_flow(flow, data, data_mask=None, flow_mask=None, sign=1.0, occlude_zero=True, valid_mode=VALID_NONE,
-               want_aux=False):
+               want_aux=False, window=()):
+    """See _splat_flow; `window` = (y0, x0, frame_h, frame_w) makes the tensors a window of a larger frame
+    (ofb_splat_s_win_fwd)."""
+    return _splat_flow(flow, data, data_mask, flow_mask, sign, occlude_zero, valid_mode, want_aux,
+                       [int(v) for v in window])
+
+
+def _splat_flow(flow, data, data_mask, flow_mask, sign, occlude_zero, valid_mode, want_aux, window):
     """S driven by a flow field (N,2,H,W).  Returns (out, density, warped_mask, valid); density and warped_mask are
     empty tensors unless `want_aux` (or autograd needs them)."""
     if data is None:
         f = flow.detach()
         out, density, wmask, _u, valid = _ops.splat_s_fwd(f[:, 0], f[:, 1], True, float(sign), None, data_mask,
-                                                          flow_mask, bool(occlude_zero), int(valid_mode), bool(want_aux))
+                                                          flow_mask, bool(occlude_zero), int(valid_mode), bool(want_aux),
+                                                          window)
         return out, density, wmask, valid
     if not want_aux and not (torch.is_grad_enabled() and (flow.requires_grad or data.requires_grad)):
         f = flow.detach()
         out, density, wmask, _u, valid = _ops.splat_s_fwd(f[:, 0], f[:, 1], True, float(sign), data.detach(), data_mask,
-                                                          flow_mask, bool(occlude_zero), int(valid_mode), False)
+                                                          flow_mask, bool(occlude_zero), int(valid_mode), False, window)
         return out, density, wmask, valid
-    return _SplatFlow.apply(flow, data, data_mask, flow_mask, float(sign), bool(occlude_zero), int(valid_mode))
+    return _SplatFlow.apply(flow, data, data_mask, flow_mask, float(sign), bool(occlude_zero), int(valid_mode), window)
 
 
 class _SplatFlow(torch.autograd.Function):
     """S with the coordinates given as the two planes of one flow tensor (no copies)."""
 
     @staticmethod
-    def forward(ctx, flow, data, data_mask, flow_mask, sign, occlude_zero, valid_mode):
+    def forward(ctx, flow, data, data_mask, flow_mask, sign, occlude_zero, valid_mode, window):
         flow = _f32c(flow)
         out, density, wmask, unocc, valid = _ops.splat_s_fwd(flow[:, 0], flow[:, 1], True, sign, data, data_mask,
-                                                             flow_mask, occlude_zero, valid_mode, True)
+                                                             flow_mask, occlude_zero, valid_mode, True, window)
         ctx.save_for_backward(flow, data, flow_mask, out, density, unocc)
-        ctx.sign, ctx.occlude_zero = sign, occlude_zero
+        ctx.sign, ctx.occlude_zero, ctx.window = sign, occlude_zero, list(window)
         ctx.mark_non_differentiable(wmask, valid)
         ctx.set_materialize_grads(False)
         return out, density, wmask, valid
@@ -349,12 +368,13 @@ class _SplatFlow(torch.autograd.Function):
         gflow = gdata = None
         if (gout is not None or gdensity is not None) and (need_gf or need_gd):
             gcoord, gd = _ops.splat_s_bwd(flow[:, 0], flow[:, 1], True, ctx.sign, data, flow_mask,
-                                          ctx.occlude_zero, out, density, unocc, gout, gdensity, need_gf, need_gd)
+                                          ctx.occlude_zero, out, density, unocc, gout, gdensity, need_gf, need_gd,
+                                          ctx.window)
             if need_gf:
                 gflow = _reduce_to(gcoord, flow)
             if need_gd:
                 gdata = _reduce_to(gd, data)
-        return gflow, gdata, None, None, None, None, None
+        return gflow, gdata, None, None, None, None, None, None
 
 
 _lib.define("warp_t_win_fwd(Tensor flow, float sign, Tensor? src, Tensor? src_mask, Tensor? flow_mask, float thresh, "

@@ -63,6 +63,10 @@ struct SplatParams {
     // SPLIT layout only (C + 1 fills the vector, e.g. RGB + density): the bad-weight channel is a plane of its own
     // behind the vectors instead of a second float4 per pixel that would be four fifths padding
     float *acc_bad;
+    // Column frame, same idea (identity: src_x0 = 0, gw = W): the tensors are columns [src_x0, src_x0 + W) of a
+    // global field of gw columns, and the accumulator stores exactly those columns.  Used by the padded 's' apply:
+    // end points are computed in the padded frame like the reference does, what lands outside the window is cut.
+    int src_x0, gw;
 };
 
 __device__ __forceinline__ void endpoint(const SplatParams &p, int n, int pix, int x, int y,
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(256, OFB_SPLAT_MINB) splat_accumulate_v1_kerne
         float X = fx, Y = fy;
         bool fm = active;
         if (p.relative) {
-            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)x);                  // utils.py:1056-1057
+            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)(x + p.src_x0));     // utils.py:1056-1057
             Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)(y + p.src_y0));
             if (p.occlude_zero) fm = fm && !is_zero_vec(fx, fy);             // utils.py:1191-1192
         }
@@ -262,8 +266,9 @@ __global__ void __launch_bounds__(256, OFB_SPLAT_MINB) splat_accumulate_v1_kerne
         // and NaN positions fail the range tests / the w > 0 test below)
         const float x0f = floorf(X), y0f = floorf(Y);
         const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
-        const int ly = yi - p.acc_y0;                                       // row inside the stored accumulator
-        const bool bx0 = (unsigned)xi < (unsigned)p.W, bx1 = (unsigned)(xi + 1) < (unsigned)p.W;
+        const int ly = yi - p.acc_y0, lx = xi - p.src_x0;                   // position inside the stored accumulator
+        const bool bx0 = (unsigned)xi < (unsigned)p.gw && (unsigned)lx < (unsigned)p.W;
+        const bool bx1 = (unsigned)(xi + 1) < (unsigned)p.gw && (unsigned)(lx + 1) < (unsigned)p.W;
         const bool by0 = (unsigned)yi < (unsigned)p.gh && (unsigned)ly < (unsigned)p.acc_h;
         const bool by1 = (unsigned)(yi + 1) < (unsigned)p.gh && (unsigned)(ly + 1) < (unsigned)p.acc_h;
         const float ax0 = __fsub_rn(__fadd_rn(x0f, 1.0f), X), ax1 = __fsub_rn(X, x0f);
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(256, OFB_SPLAT_MINB) splat_accumulate_v1_kerne
         const float w_sw = (fm && bx0 && by1) ? __fmul_rn(ay1, ax0) : 0.0f;
         const float w_se = (fm && bx1 && by1) ? __fmul_rn(ay1, ax1) : 0.0f;
         const bool p_nw = w_nw > 0.0f, p_ne = w_ne > 0.0f, p_sw = w_sw > 0.0f, p_se = w_se > 0.0f;   // adding +0 is a no-op
-        const int o = (int)((unsigned)ly * (unsigned)p.W + (unsigned)xi);
+        const int o = (int)((unsigned)ly * (unsigned)p.W + (unsigned)lx);
 
         const float *d = cur.d;
         const float badf = (HAS_BAD && cur.dm == 0) ? 1.0f : 0.0f;
@@ -466,6 +471,7 @@ struct SplatBwdParams {
     const float *gout, *gdensity;
     float *gcx, *gcy; int64_t gcoord_bs; float *gdata;
     int N, C, H, W;
+    int src_y0, src_x0, gh, gw;      // window frame as in SplatParams (v1 kernels only; identity = 0, 0, H, W)
 };
 
 constexpr int kMaxC = 8;   // channels held in registers by the v0 adjoint; larger C is chunked
@@ -708,8 +714,8 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
         float X = fx, Y = fy;
         bool fm = true;
         if (p.relative) {
-            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)x);
-            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)y);
+            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)(x + p.src_x0));
+            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)(y + p.src_y0));
             if (p.occlude_zero) fm = !is_zero_vec(fx, fy);
         }
         fm = fm && (fms[r] != 0);
@@ -721,20 +727,25 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
             const float *dat = dats[r];
             const float x0f = floorf(X), y0f = floorf(Y);
             const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
-            const bool bx[2] = {(unsigned)xi < (unsigned)p.W, (unsigned)(xi + 1) < (unsigned)p.W};
-            const bool by[2] = {(unsigned)yi < (unsigned)p.H, (unsigned)(yi + 1) < (unsigned)p.H};
+            // in-frame tests decide the weights (utils.py:1110-1111); a tap outside the stored window exists in the
+            // frame but was cut away with its gradient, so it contributes nothing
+            const bool bx[2] = {(unsigned)xi < (unsigned)p.gw, (unsigned)(xi + 1) < (unsigned)p.gw};
+            const bool by[2] = {(unsigned)yi < (unsigned)p.gh, (unsigned)(yi + 1) < (unsigned)p.gh};
+            const int lx = xi - p.src_x0, ly = yi - p.src_y0;
+            const bool sx[2] = {(unsigned)lx < (unsigned)p.W, (unsigned)(lx + 1) < (unsigned)p.W};
+            const bool sy[2] = {(unsigned)ly < (unsigned)p.H, (unsigned)(ly + 1) < (unsigned)p.H};
             const float ax[2] = {__fsub_rn(__fadd_rn(x0f, 1.0f), X), __fsub_rn(X, x0f)};
             const float ay[2] = {__fsub_rn(__fadd_rn(y0f, 1.0f), Y), __fsub_rn(Y, y0f)};
             const float wx[2] = {bx[0] ? ax[0] : 0.0f, bx[1] ? ax[1] : 0.0f};      // utils.py:1110
             const float wy[2] = {by[0] ? ay[0] : 0.0f, by[1] ? ay[1] : 0.0f};      // utils.py:1111
-            const int o = yi * p.W + xi;
+            const int o = ly * p.W + lx;
             float Gv[2][2];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     Gv[a][b] = 0.0f;
-                    if (!(bx[b] && by[a])) continue;                            // contributes to nothing
+                    if (!(bx[b] && by[a] && sx[b] && sy[a])) continue;          // contributes to nothing
                     float g[KG];
                     load_g<KG>(Gn, o + a * p.W + b, g);
                     const float w = __fmul_rn(wy[a], wx[b]);
@@ -834,16 +845,21 @@ extern "C" int64_t ofb_splat_s_workspace(int N, int C, int H, int W, int has_dat
     return (int64_t)N * (C + 2) * H * W;
 }
 
-extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
-                               const float *data, int64_t data_bs,
-                               const uint8_t *data_mask, int64_t data_mask_bs,
-                               const uint8_t *flow_mask, int64_t flow_mask_bs,
-                               int occlude_zero, float *acc, int64_t acc_floats,
-                               float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
-                               uint8_t *valid, int valid_mode,
-                               int N, int C, int H, int W, void *stream)
+// win = {src_y0, src_x0, gh, gw}: the H x W tensors are the window at (src_y0, src_x0) of a gh x gw frame in which
+// the end points are computed and tested; what lands outside the window is dropped
+static int splat_fwd_impl(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
+                          const float *data, int64_t data_bs,
+                          const uint8_t *data_mask, int64_t data_mask_bs,
+                          const uint8_t *flow_mask, int64_t flow_mask_bs,
+                          int occlude_zero, float *acc, int64_t acc_floats,
+                          float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
+                          uint8_t *valid, int valid_mode,
+                          int N, int C, int H, int W, const int *win, void *stream)
 {
     if (!cx || !cy || !acc || N <= 0 || C < 0 || (C > 0 && (!data || !out))) return OFB_EINVAL;
+    const bool windowed = !(win[0] == 0 && win[1] == 0 && win[2] == H && win[3] == W);
+    if (win[0] < 0 || win[1] < 0 || win[0] + H > win[2] || win[1] + W > win[3]) return OFB_EINVAL;
+    if (windowed && !relative) return OFB_EINVAL;
     if (occlude_zero && !relative) return OFB_EINVAL;
     if (valid && valid_mode != OFB_VALID_GT && valid_mode != OFB_VALID_EQ1) return OFB_EINVAL;
     if (H < 1 || W < 1) return OFB_ESHAPE;
@@ -851,7 +867,7 @@ extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_b
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SplatParams p{cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs,
                   flow_mask, flow_mask_bs, occlude_zero, acc, out, density, warped_mask, unocc,
-                  valid, valid_mode, N, C, H, W, 0, H, 0, H, nullptr};
+                  valid, valid_mode, N, C, H, W, win[0], win[2], win[0], H, nullptr, win[1], win[3]};
     SplatV1 k;
     static const bool planar_only = getenv("OFB_SPLAT_PLANAR") != nullptr;
     if (!planar_only && splat_v1(C, data_mask != nullptr, &k)) {
@@ -879,6 +895,7 @@ extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_b
             return 0;
         }
     }
+    if (windowed) return OFB_EINVAL;                                       // the planar kernels know no window
     if (acc_floats < (int64_t)N * (C + 2) * H * W) return OFB_EINVAL;     // planar path needs C+2 planes per item
     cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)N * (C + 2) * H * W, st);
     if (e != cudaSuccess) return (int)e;
@@ -891,12 +908,85 @@ extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_b
     return 0;
 }
 
+extern "C" int ofb_splat_s_fwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
+                               const float *data, int64_t data_bs,
+                               const uint8_t *data_mask, int64_t data_mask_bs,
+                               const uint8_t *flow_mask, int64_t flow_mask_bs,
+                               int occlude_zero, float *acc, int64_t acc_floats,
+                               float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
+                               uint8_t *valid, int valid_mode,
+                               int N, int C, int H, int W, void *stream)
+{
+    const int win[4] = {0, 0, H, W};
+    return splat_fwd_impl(cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs, flow_mask,
+                          flow_mask_bs, occlude_zero, acc, acc_floats, out, density, warped_mask, unocc, valid,
+                          valid_mode, N, C, H, W, win, stream);
+}
+
+extern "C" int ofb_splat_s_win_fwd(const float *cx, const float *cy, int64_t coord_bs, float sign,
+                                   const float *data, int64_t data_bs,
+                                   const uint8_t *data_mask, int64_t data_mask_bs,
+                                   const uint8_t *flow_mask, int64_t flow_mask_bs,
+                                   int occlude_zero, float *acc, int64_t acc_floats,
+                                   float *out, float *density, uint8_t *warped_mask, uint8_t *unocc,
+                                   uint8_t *valid, int valid_mode,
+                                   int N, int C, int H, int W, const int *window, void *stream)
+{
+    if (!window) return OFB_EINVAL;
+    return splat_fwd_impl(cx, cy, coord_bs, 1, sign, data, data_bs, data_mask, data_mask_bs, flow_mask,
+                          flow_mask_bs, occlude_zero, acc, acc_floats, out, density, warped_mask, unocc, valid,
+                          valid_mode, N, C, H, W, window, stream);
+}
+
 // floats of workspace ofb_splat_s_bwd wants (0: none, the generic gather is used)
 extern "C" int64_t ofb_splat_s_bwd_workspace(int N, int C, int H, int W)
 {
     SplatBwdV1 k;
     if (N <= 0 || H <= 0 || W <= 0 || !splat_bwd_v1(C, &k)) return 0;
     return (int64_t)N * H * W * k.kg;
+}
+
+static int splat_bwd_impl(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
+                          const float *data, int64_t data_bs,
+                          const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
+                          const float *out, const float *density, const uint8_t *unocc,
+                          const float *gout, const float *gdensity,
+                          float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                          float *work, int64_t work_floats,
+                          int N, int C, int H, int W, const int *win, void *stream)
+{
+    if (!cx || !cy || !density || N <= 0 || C < 0) return OFB_EINVAL;
+    const bool windowed = !(win[0] == 0 && win[1] == 0 && win[2] == H && win[3] == W);
+    if (win[0] < 0 || win[1] < 0 || win[0] + H > win[2] || win[1] + W > win[3]) return OFB_EINVAL;
+    if (windowed && !relative) return OFB_EINVAL;
+    if (C > 0 && (!data || !out || !gout)) return OFB_EINVAL;
+    if ((gcx == nullptr) != (gcy == nullptr)) return OFB_EINVAL;
+    if (H < 1 || W < 1) return OFB_ESHAPE;
+    if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
+    if (!gcx && !gdata) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SplatBwdParams p{cx, cy, coord_bs, relative, sign, data, data_bs, flow_mask, flow_mask_bs, occlude_zero,
+                     out, density, unocc, gout, gdensity, gcx, gcy, gcoord_bs, gdata, N, C, H, W,
+                     win[0], win[1], win[2], win[3]};
+    const dim3 block(32, 8);
+    const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
+    SplatBwdV1 k;
+    if (work && splat_bwd_v1(C, &k) && work_floats >= (int64_t)N * H * W * k.kg) {
+        k.pre<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
+        OFB_CHECK_LAUNCH();
+        k.gat<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
+        OFB_CHECK_LAUNCH();
+        return 0;
+    }
+    if (windowed) return OFB_EINVAL;                  // the generic gather knows no window
+    int c0 = 0;
+    do {
+        const int cn = (C - c0 < kMaxC) ? (C - c0) : kMaxC;
+        splat_bwd_kernel<<<grid, block, 0, st>>>(p, c0, cn, c0 == 0);
+        OFB_CHECK_LAUNCH();
+        c0 += kMaxC;
+    } while (c0 < C);
+    return 0;
 }
 
 extern "C" int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_bs, int relative, float sign,
@@ -908,33 +998,25 @@ extern "C" int ofb_splat_s_bwd(const float *cx, const float *cy, int64_t coord_b
                                float *work, int64_t work_floats,
                                int N, int C, int H, int W, void *stream)
 {
-    if (!cx || !cy || !density || N <= 0 || C < 0) return OFB_EINVAL;
-    if (C > 0 && (!data || !out || !gout)) return OFB_EINVAL;
-    if ((gcx == nullptr) != (gcy == nullptr)) return OFB_EINVAL;
-    if (H < 1 || W < 1) return OFB_ESHAPE;
-    if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
-    if (!gcx && !gdata) return 0;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    SplatBwdParams p{cx, cy, coord_bs, relative, sign, data, data_bs, flow_mask, flow_mask_bs, occlude_zero,
-                     out, density, unocc, gout, gdensity, gcx, gcy, gcoord_bs, gdata, N, C, H, W};
-    const dim3 block(32, 8);
-    const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
-    SplatBwdV1 k;
-    if (work && splat_bwd_v1(C, &k) && work_floats >= (int64_t)N * H * W * k.kg) {
-        k.pre<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
-        OFB_CHECK_LAUNCH();
-        k.gat<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
-        OFB_CHECK_LAUNCH();
-        return 0;
-    }
-    int c0 = 0;
-    do {
-        const int cn = (C - c0 < kMaxC) ? (C - c0) : kMaxC;
-        splat_bwd_kernel<<<grid, block, 0, st>>>(p, c0, cn, c0 == 0);
-        OFB_CHECK_LAUNCH();
-        c0 += kMaxC;
-    } while (c0 < C);
-    return 0;
+    const int win[4] = {0, 0, H, W};
+    return splat_bwd_impl(cx, cy, coord_bs, relative, sign, data, data_bs, flow_mask, flow_mask_bs, occlude_zero, out,
+                          density, unocc, gout, gdensity, gcx, gcy, gcoord_bs, gdata, work, work_floats, N, C, H, W,
+                          win, stream);
+}
+
+extern "C" int ofb_splat_s_win_bwd(const float *cx, const float *cy, int64_t coord_bs, float sign,
+                                   const float *data, int64_t data_bs,
+                                   const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
+                                   const float *out, const float *density, const uint8_t *unocc,
+                                   const float *gout, const float *gdensity,
+                                   float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                                   float *work, int64_t work_floats,
+                                   int N, int C, int H, int W, const int *window, void *stream)
+{
+    if (!window) return OFB_EINVAL;
+    return splat_bwd_impl(cx, cy, coord_bs, 1, sign, data, data_bs, flow_mask, flow_mask_bs, occlude_zero, out,
+                          density, unocc, gout, gdensity, gcx, gcy, gcoord_bs, gdata, work, work_floats, N, C, H, W,
+                          window, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -968,7 +1050,8 @@ extern "C" int ofb_splat_s_band_accumulate(const float *cx, const float *cy, int
     cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)N * acc_h * W * k.kp, st);
     if (e != cudaSuccess) return (int)e;
     SplatParams p{cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs, flow_mask, flow_mask_bs,
-                  occlude_zero, acc, nullptr, nullptr, nullptr, nullptr, nullptr, 0, N, C, H, W, src_y0, gh, acc_y0, acc_h};
+                  occlude_zero, acc, nullptr, nullptr, nullptr, nullptr, nullptr, 0, N, C, H, W, src_y0, gh, acc_y0, acc_h,
+                  nullptr, 0, W};
     k.acc<<<dim3((W + 63) / 64, (H + 4 * kSplatRows - 1) / (4 * kSplatRows), N), 256, 0, st>>>(p, 0);
     OFB_CHECK_LAUNCH();
     return 0;
@@ -991,7 +1074,7 @@ extern "C" int ofb_splat_s_band_normalise(const float *cx, const float *cy, int6
     if (src_y0 < acc_y0 || src_y0 + H > acc_y0 + acc_h || acc_y0 + acc_h > gh || N > 65535) return OFB_EINVAL;
     SplatParams p{cx, cy, coord_bs, relative, 1.0f, data, data_bs, data_mask, data_mask_bs, flow_mask, flow_mask_bs,
                   occlude_zero, const_cast<float *>(acc), out, density, warped_mask, unocc, valid, valid_mode,
-                  N, C, H, W, src_y0, gh, acc_y0, acc_h};
+                  N, C, H, W, src_y0, gh, acc_y0, acc_h, nullptr, 0, W};
     k.norm<<<dim3((W + 63) / 64, (H + 4 * kNormRows - 1) / (4 * kNormRows), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, 0);
     OFB_CHECK_LAUNCH();
     return 0;

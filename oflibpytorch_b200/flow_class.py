@@ -435,6 +435,14 @@ class Flow(object):
             # (flow_class.py:917-918) is materialised.
             return self._finish_apply(*self._warp_window(t, mask, need_valid, padding), target if return_flow else None,
                                       return_dtype, return_2d, return_3d, return_valid_area)
+        if padding is not None and cut and self._ref == 's' and consider_mask and t.shape[1] <= 6:
+            # Fused padding for 's' flows.  The reference pads the flow with replicated vectors and
+            # a False mask (flow_class.py:905-914), splats the whole padded frame and cuts the window back out
+            # (:917-918).  With consider_mask the padded sources are ignored, so only the window is splatted -- in
+            # the padded FRAME (ofb_splat_s_win_fwd: end points y + top + f, x + left + f, the reference's floats),
+            # dropping what lands outside the window.
+            return self._finish_apply(*self._splat_window(t, mask, need_valid, padding), target if return_flow else None,
+                                      return_dtype, return_2d, return_3d, return_valid_area)
         flow = self
         top = left = 0
         if padding is not None:                                     # flow_class.py:905-914
@@ -489,6 +497,28 @@ class Flow(object):
             return out, valid
         out, valid = _ops.warp_t_win(self._vecs, t, [top, left, th, tw, 0, 0, th, tw], mask if need_valid else None,
                                      self._mask if need_valid else None, want_valid=need_valid)
+        return out, (valid if need_valid else None)
+
+    def _splat_window(self, t: torch.Tensor, mask: Optional[torch.Tensor], need_valid: bool, padding: list):
+        """'s' apply of the (top, left) window of a larger target, with apply_flow's zero-flow early-out."""
+        top, left = padding[0], padding[2]
+        fh, fw = self.shape[1], self.shape[2]
+        th, tw = t.shape[-2:]
+        tw_ = t[..., top:top + fh, left:left + fw]
+        payload_mask = None
+        if need_valid:                                               # flow_class.py:880-895 restricted to the window
+            payload_mask = self._mask if mask is None else (mask[..., top:top + fh, left:left + fw] & self._mask)
+        if self._all_zero(thresholded=True, masked=False):           # utils.py:497-498, then the cut
+            n = max(t.shape[0], self.shape[0])
+            valid = None
+            if need_valid:
+                valid = payload_mask if payload_mask.shape[0] == n else payload_mask.expand(n, -1, -1)
+            return (tw_ if tw_.shape[0] == n else tw_.expand(n, -1, -1, -1)), valid
+        same = payload_mask is self._mask
+        out, _d, _w, valid = _ops.splat_flow(self._vecs, tw_, None if (same or not need_valid) else payload_mask,
+                                             self._mask, sign=1.0, occlude_zero=True,
+                                             valid_mode=VALID_GT if need_valid else VALID_NONE,
+                                             window=(top, left, th, tw))
         return out, (valid if need_valid else None)
 
     def _finish_apply(self, warped, valid, flow_target, return_dtype, return_2d, return_3d, return_valid_area):

@@ -185,11 +185,12 @@ def test_fused_padding_is_bit_identical_to_the_padded_path():
 
 def test_padded_s_apply_with_cut_equals_the_reference_padded_path():
     """Flow.apply(padding=..., cut=True) for 's' flows: the reference pads flow (replicate) and mask (False), splats the
-    whole padded frame and cuts.  Splatting only the window would give the same masks but not the same floats: the
-    end points are computed in the padded frame (x + left + f rounds differently from x + f) and where the density is
-    below the 1e-3 clamp that difference is amplified past the tolerance (measured: 1.6e-3 at one pixel of 17 202
-    here).  So the padded frame is kept; checked against the oracle, which follows the reference, with flows large
-    enough to push pixels out of the window, with a Flow target and with consider_mask=False."""
+    whole padded frame and cuts.  With consider_mask the padded sources are ignored, so this package splats only the
+    window -- but in the padded FRAME (ofb_splat_s_win_fwd): computing the end points as x + f instead of
+    x + left + f rounds differently, and where the density is below the 1e-3 clamp that difference is amplified past
+    the tolerance (measured: 1.6e-3 at one pixel of 17 202 here).  Checked against the oracle, which follows the
+    reference, with flows large enough to push pixels out of the window, gradients, a Flow target, and
+    consider_mask=False (which keeps the padded path)."""
     o = orc()
     n, c, h, w = 2, 3, 47, 61
     pad = [6, 4, 9, 3]
@@ -205,6 +206,14 @@ def test_padded_s_apply_with_cut_equals_the_reference_padded_path():
                                                                  padding=pad, cut=True, consider_mask=consider)
         assert_close(og, oo, 'padded s apply, consider_mask=%s' % consider)
         assert_mask_equal(vg, vo, 'padded s valid, consider_mask=%s' % consider)
+    # gradients through the windowed splat (flow and the WHOLE padded image: zero outside the window)
+    gout = torch.rand(n, c, h, w, generator=gen(995))
+    fo, bo = flow.clone().requires_grad_(), big.clone().requires_grad_()
+    o.OFlow(fo, 's', fmask).apply(bo, bigm, padding=pad, cut=True).backward(gout)
+    fg, bg = flow.cuda().requires_grad_(), big.cuda().requires_grad_()
+    of().Flow(fg, 's', fmask.cuda()).apply(bg, bigm.cuda(), padding=pad, cut=True).backward(gout.cuda())
+    assert_grad_close(fg.grad, fo.grad, 'padded s apply, gflow')
+    assert_grad_close(bg.grad, bo.grad, 'padded s apply, gimage')
     fb = smooth_flow(n, h + pad[0] + pad[1], w + pad[2] + pad[3], 2.0, 994)
     ro = o.OFlow(flow, 's', fmask).apply(o.OFlow(fb, 's', bigm), padding=pad, cut=True)
     rg = of().Flow(flow.cuda(), 's', fmask.cuda()).apply(of().Flow(fb.cuda(), 's', bigm.cuda()), padding=pad, cut=True)
