@@ -672,9 +672,11 @@ __device__ __forceinline__ void load_g(const float *__restrict__ G, int q, float
     }
 }
 
-template <int C, int KG>
+template <int C, int KG, bool WIN>
 __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdParams p, const float *__restrict__ G)
 {
+    // WIN = false (compile time): the tensors ARE the frame, no origin shift and no second range test
+    const int fx0 = WIN ? p.src_x0 : 0, fy0 = WIN ? p.src_y0 : 0, gw = WIN ? p.gw : p.W, gh = WIN ? p.gh : p.H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
     const int y0 = blockIdx.y * (4 * kPreRows) + (warp >> 1) * kPreRows;
@@ -714,8 +716,8 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
         float X = fx, Y = fy;
         bool fm = true;
         if (p.relative) {
-            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)(x + p.src_x0));
-            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)(y + p.src_y0));
+            X = __fadd_rn(__fmul_rn(p.sign, fx), (float)(x + fx0));
+            Y = __fadd_rn(__fmul_rn(p.sign, fy), (float)(y + fy0));
             if (p.occlude_zero) fm = !is_zero_vec(fx, fy);
         }
         fm = fm && (fms[r] != 0);
@@ -729,11 +731,11 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
             const int xi = __float2int_rd(X), yi = __float2int_rd(Y);
             // in-frame tests decide the weights (utils.py:1110-1111); a tap outside the stored window exists in the
             // frame but was cut away with its gradient, so it contributes nothing
-            const bool bx[2] = {(unsigned)xi < (unsigned)p.gw, (unsigned)(xi + 1) < (unsigned)p.gw};
-            const bool by[2] = {(unsigned)yi < (unsigned)p.gh, (unsigned)(yi + 1) < (unsigned)p.gh};
-            const int lx = xi - p.src_x0, ly = yi - p.src_y0;
-            const bool sx[2] = {(unsigned)lx < (unsigned)p.W, (unsigned)(lx + 1) < (unsigned)p.W};
-            const bool sy[2] = {(unsigned)ly < (unsigned)p.H, (unsigned)(ly + 1) < (unsigned)p.H};
+            const bool bx[2] = {(unsigned)xi < (unsigned)gw, (unsigned)(xi + 1) < (unsigned)gw};
+            const bool by[2] = {(unsigned)yi < (unsigned)gh, (unsigned)(yi + 1) < (unsigned)gh};
+            const int lx = xi - fx0, ly = yi - fy0;
+            const bool sx[2] = {!WIN || (unsigned)lx < (unsigned)p.W, !WIN || (unsigned)(lx + 1) < (unsigned)p.W};
+            const bool sy[2] = {!WIN || (unsigned)ly < (unsigned)p.H, !WIN || (unsigned)(ly + 1) < (unsigned)p.H};
             const float ax[2] = {__fsub_rn(__fadd_rn(x0f, 1.0f), X), __fsub_rn(X, x0f)};
             const float ay[2] = {__fsub_rn(__fadd_rn(y0f, 1.0f), Y), __fsub_rn(Y, y0f)};
             const float wx[2] = {bx[0] ? ax[0] : 0.0f, bx[1] ? ax[1] : 0.0f};      // utils.py:1110
@@ -784,13 +786,13 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
 
 typedef void (*SplatBwdPre)(const SplatBwdParams, float *);
 typedef void (*SplatBwdGat)(const SplatBwdParams, const float *);
-struct SplatBwdV1 { SplatBwdPre pre; SplatBwdGat gat; int kg; };
+struct SplatBwdV1 { SplatBwdPre pre; SplatBwdGat gat, gat_win; int kg; };
 
 template <int C>
 static SplatBwdV1 splat_bwd_v1_for()
 {
     constexpr int KG = (C + 1 <= 2) ? 2 : ((C + 1 <= 4) ? 4 : 8);
-    return {splat_bwd_prepass_kernel<C, KG>, splat_bwd_gather_kernel<C, KG>, KG};
+    return {splat_bwd_prepass_kernel<C, KG>, splat_bwd_gather_kernel<C, KG, false>, splat_bwd_gather_kernel<C, KG, true>, KG};
 }
 
 static bool splat_bwd_v1(int C, SplatBwdV1 *k)
@@ -974,7 +976,7 @@ static int splat_bwd_impl(const float *cx, const float *cy, int64_t coord_bs, in
     if (work && splat_bwd_v1(C, &k) && work_floats >= (int64_t)N * H * W * k.kg) {
         k.pre<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
         OFB_CHECK_LAUNCH();
-        k.gat<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
+        (windowed ? k.gat_win : k.gat)<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, st>>>(p, work);
         OFB_CHECK_LAUNCH();
         return 0;
     }
