@@ -341,10 +341,30 @@ def main():
     # ---------------------------------------------------------------- end to end with host buffers
     e2e = None
     if not args.no_e2e:
-        host_in = [x.detach().cpu().pin_memory() for x in (flow, img, mask, tmask, gout)]
-        o, v, gf, gi = gpu_step(of, flow, img, mask, tmask, gout)
-        host_out = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (o, v, gf, gi)]
-        del o, v, gf, gi
+        # pinned host copies of the whole batch (9 GB per rank at the named config); if any rank cannot pin that much
+        # (8 ranks on one host), every rank falls back to a quarter of the batch -- agreed collectively so that the
+        # barriers below stay matched
+        e2e_n, host_in, host_out = n, None, None
+        for attempt_n in (n, max(1, n // 4)):
+            ok = 1
+            try:
+                host_in = [x[:attempt_n].detach().cpu().pin_memory() for x in (flow, img, mask, tmask, gout)]
+                o, v, gf, gi = gpu_step(of, flow[:attempt_n].detach(), img[:attempt_n].detach(), mask[:attempt_n],
+                                        tmask[:attempt_n], gout[:attempt_n])
+                host_out = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for x in (o, v, gf, gi)]
+                del o, v, gf, gi
+            except (RuntimeError, MemoryError):
+                ok, host_in, host_out = 0, None, None
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                e2e_n = attempt_n
+                break
+            host_in = host_out = None
+        if host_in is None:
+            raise RuntimeError('bench.py: could not pin the host buffers of the end-to-end path on every rank')
+        px_e2e = e2e_n * H * W
         h2d = sum(x.numel() * x.element_size() for x in host_in)
         d2h = sum(x.numel() * x.element_size() for x in host_out)
 
@@ -369,10 +389,11 @@ def main():
         t2 = torch.tensor([s0.elapsed_time(s1) / k2], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * px / (float(t2.item()) * 1e-3) / 1e6, 'unit': 'Mpix/s',
+        e2e = {'value': world * px_e2e / (float(t2.item()) * 1e-3) / 1e6, 'unit': 'Mpix/s',
                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': float(t2.item()),
-               'steps': k2, 'how': 'oflibpytorch_b200.streaming.HostWarpPipeline, chunk %d, pinned host buffers, '
-                                   'H2D/compute/D2H on three streams' % args.e2e_chunk}
+               'steps': k2, 'batch_per_gpu': e2e_n,
+               'how': 'oflibpytorch_b200.streaming.HostWarpPipeline, chunk %d, pinned host buffers, '
+                      'H2D/compute/D2H on three streams' % args.e2e_chunk}
         del host_in, host_out
 
     # ---------------------------------------------------------------- secondary workloads (information only)
