@@ -462,7 +462,7 @@ struct WarpBwdParams {
 // accumulation was rejected: float atomicAdd on shared memory is a CAS loop on sm_100 (ATOMS.CAST.SPIN, ~8 clk per
 // warp-op, tools/microbench.cu).
 #ifndef OFB_BWD_ROWS
-#define OFB_BWD_ROWS 8
+#define OFB_BWD_ROWS 4
 #endif
 #ifndef OFB_BWD_MINB
 #define OFB_BWD_MINB 4
