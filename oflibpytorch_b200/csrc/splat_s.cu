@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const SplatParams 
 // launches (OFB_SPLAT_CHUNK_MB splits it): per-item passes meant to keep the accumulator in the L2 were measured
 // slower, with and without a persisting access-policy window, and so was a persistent kernel sweeping an L2-sized
 // ring of accumulator rows (profiles/r01_ring_splat_experiment.patch).
-constexpr int kSplatRows = 8;      // source rows per thread; CTA tile = 64 x 32 (2 warps across x, 4 across y)
+#ifndef OFB_SPLAT_ROWS
+#define OFB_SPLAT_ROWS 8
+#endif
+constexpr int kSplatRows = OFB_SPLAT_ROWS;   // source rows per thread; CTA tile = 64 x 4*rows (2 warps across x, 4 across y)
 
 template <int KP> struct AccVec { float v[KP]; };
 
