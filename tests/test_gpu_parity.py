@@ -356,3 +356,24 @@ def test_host_pipeline_matches_direct_call():
     out2, valid2, g1, g2 = pipe.run(pin[0], pin[1], 't', pin[2], pin[3])      # forward only
     torch.cuda.synchronize()
     assert g1 is None and g2 is None and bit_equal(out2, og) and torch.equal(valid2, vg.cpu())
+
+
+def test_host_pipeline_source_reference_flows():
+    """the same pipeline with ref 's' (splat path): chunked result == one direct call; masks bit-exact"""
+    from oflibpytorch_b200.streaming import HostWarpPipeline
+    n, c, h, w = 5, 3, 64, 80
+    flow = smooth_flow(n, h, w, 4.0, 810)
+    img = torch.rand(n, c, h, w, generator=gen(811))
+    gout = torch.rand(n, c, h, w, generator=gen(812))
+    fmask, tmask = holed_mask(n, h, w, 813), holed_mask(n, h, w, 814)
+    pipe = HostWarpPipeline(torch.device('cuda', 0), chunk=3)
+    pin = [t.pin_memory() for t in (flow, img, fmask, tmask, gout)]
+    out_h, valid_h, gf_h, gi_h = pipe.run(pin[0], pin[1], 's', pin[2], pin[3], pin[4])
+    torch.cuda.synchronize()
+    fg, ig = cu(flow).requires_grad_(), cu(img).requires_grad_()
+    og, vg = of().Flow(fg, 's', cu(fmask)).apply(ig, cu(tmask), return_valid_area=True)
+    og.backward(cu(gout))
+    assert_close(out_h, og, 'out')
+    assert torch.equal(valid_h, vg.cpu())
+    assert_grad_close(gf_h, fg.grad, 'gflow')
+    assert_grad_close(gi_h, ig.grad, 'gimg')
