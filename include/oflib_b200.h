@@ -207,6 +207,24 @@ int ofb_splat_s_band_normalise(const float *cx, const float *cy, int64_t coord_b
                                uint8_t *valid, int valid_mode,
                                int N, int C, int H, int W, const int *band, void *stream);
 
+/* Row-band adjoint of the splat (one oversized field split over GPUs, see ofb_splat_s_band_accumulate).
+ *   1. ofb_splat_s_band_bwd_prepass on the rank's own target rows: G (N,H,W,KG), KG = ofb_splat_s_kg(C), holds per
+ *      target pixel {gout_c / max(den, 1e-3), d loss / d den}; out/density/unocc are the band's forward results.
+ *   2. the caller copies the neighbours' halo rows of G in (sharding.exchange_row_halos);
+ *   3. ofb_splat_s_band_bwd_gather for the rank's own sources against the extended G:
+ *      band (host, 4 ints) = {src_y0, global_h, acc_y0, acc_h}, G = (N, acc_h, W, KG) = frame rows
+ *      [acc_y0, acc_y0 + acc_h); unocc / gout are the rank's own rows (gout only read where unocc is set). */
+int ofb_splat_s_kg(int C);
+int ofb_splat_s_band_bwd_prepass(const float *out, const float *density, const uint8_t *unocc,
+                                 const float *gout, const float *gdensity, float *G,
+                                 int N, int C, int H, int W, void *stream);
+int ofb_splat_s_band_bwd_gather(const float *cx, const float *cy, int64_t coord_bs, float sign,
+                                const float *data, int64_t data_bs,
+                                const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
+                                const float *G, const uint8_t *unocc, const float *gout,
+                                float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                                int N, int C, int H, int W, const int *band, void *stream);
+
 /* Point sampling of a flow field -- the sparse half of track_pts (utils.py:1003-1019): out[n,m,:] = (flow_y, flow_x)
  * bilinearly interpolated at pts[n,m,:] = (y, x) with grid_sample(align_corners=True, zeros) semantics.
  *   flow (N|1, 2, H, W); pts, out (N, M, 2).  The adjoint yields gflow (N|1,2,H,W; zero-filled by the call; stride 0

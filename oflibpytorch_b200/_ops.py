@@ -535,9 +535,9 @@ def splat_band_accumulate(flow, data, data_mask, flow_mask, sign, occlude_zero, 
     return acc
 
 
-def splat_band_normalise(acc, flow, data, data_mask, flow_mask, occlude_zero, valid_mode, band):
+def splat_band_normalise(acc, flow, data, data_mask, flow_mask, occlude_zero, valid_mode, band, want_aux=False):
     """Row-band splat, step 2: normalise this rank's own rows from the (halo-summed) accumulator.
-    Returns (out (N,C,H,W), valid (N,H,W) or empty)."""
+    Returns (out (N,C,H,W), valid (N,H,W) or empty); with `want_aux` also (density, unocc) for the adjoint."""
     flow = _f32c(flow.detach())
     data = None if data is None else _f32c(data.detach())
     data_mask, flow_mask = _maskc(data_mask), _maskc(flow_mask)
@@ -549,13 +549,51 @@ def splat_band_normalise(acc, flow, data, data_mask, flow_mask, occlude_zero, va
     with torch.cuda.device(flow.device):
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=flow.device)
         valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=flow.device)
+        density = torch.empty((n, h, w) if want_aux else (0,), dtype=torch.float32, device=flow.device)
+        unocc = torch.empty((n, h, w) if (want_aux and occlude_zero) else (0,), dtype=torch.bool, device=flow.device)
         cx, cy = flow[:, 0], flow[:, 1]
         _call("ofb_splat_s_band_normalise", _p(cx), _p(cy), 0 if (flow.shape[0] == 1 and n > 1) else 2 * hw, 1,
               _p(data) if c else None, _bs(data, n, c * hw), _p(data_mask), _bs(data_mask, n, hw),
               _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(acc.contiguous()), _p(out) if c else None,
-              None, None, None, _p(valid) if want_valid else None, valid_mode, n, c, h, w,
+              _p(density) if want_aux else None, None, _p(unocc) if (want_aux and occlude_zero) else None,
+              _p(valid) if want_valid else None, valid_mode, n, c, h, w,
               (ctypes.c_int * 4)(*[int(v) for v in band]), _stream())
+    if want_aux:
+        return out, valid, density, (unocc if occlude_zero else None)
     return out, valid
+
+
+def splat_band_bwd_prepass(out, density, unocc, gout):
+    """Row-band splat adjoint, step 1: G (N,H,W,KG) for this rank's own target rows (ofb_splat_s_band_bwd_prepass)."""
+    out, density, gout = _f32c(out), _f32c(density), _f32c(gout)
+    n, c, h, w = out.shape
+    kg = int(_native.lib().ofb_splat_s_kg(c))
+    if kg == 0:
+        raise ValueError("oflibpytorch_b200: the row-band splat adjoint supports 1..7 payload channels")
+    with torch.cuda.device(out.device):
+        g = torch.empty((n, h, w, kg), dtype=torch.float32, device=out.device)
+        _call("ofb_splat_s_band_bwd_prepass", _p(out), _p(density), _p(unocc), _p(gout), None, _p(g), n, c, h, w,
+              _stream())
+    return g
+
+
+def splat_band_bwd_gather(flow, data, flow_mask, occlude_zero, g_ext, unocc, gout, band, need_gflow, need_gdata):
+    """Row-band splat adjoint, step 3: gradients of this rank's own sources against the halo-extended G
+    (ofb_splat_s_band_bwd_gather).  band = (src_y0, global_h, acc_y0, acc_h).  Returns (gflow, gdata)."""
+    flow, data, gout = _f32c(flow.detach()), _f32c(data.detach()), _f32c(gout)
+    flow_mask = _maskc(flow_mask)
+    n, c, h, w = data.shape
+    hw = h * w
+    with torch.cuda.device(flow.device):
+        gflow = torch.empty((n, 2, h, w) if need_gflow else (0,), dtype=torch.float32, device=flow.device)
+        gdata = torch.empty((n, c, h, w) if need_gdata else (0,), dtype=torch.float32, device=flow.device)
+        gcx = ctypes.c_void_p(gflow.data_ptr()) if need_gflow else None
+        gcy = ctypes.c_void_p(gflow.data_ptr() + 4 * hw) if need_gflow else None
+        _call("ofb_splat_s_band_bwd_gather", _p(flow[:, 0]), _p(flow[:, 1]), 2 * hw, 1.0, _p(data), c * hw,
+              _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(g_ext.contiguous()),
+              _p(unocc) if (unocc is not None and unocc.numel()) else None, _p(gout), gcx, gcy, 2 * hw,
+              _p(gdata) if need_gdata else None, n, c, h, w, (ctypes.c_int * 4)(*[int(v) for v in band]), _stream())
+    return gflow, gdata
 
 
 def splat_xy(x, y, data, mask=None):

@@ -475,6 +475,7 @@ struct SplatBwdParams {
     float *gcx, *gcy; int64_t gcoord_bs; float *gdata;
     int N, C, H, W;
     int src_y0, src_x0, gh, gw;      // window frame as in SplatParams (v1 kernels only; identity = 0, 0, H, W)
+    int acc_y0, acc_h;               // rows of the frame that G stores (window path; padded apply: src_y0, H)
 };
 
 constexpr int kMaxC = 8;   // channels held in registers by the v0 adjoint; larger C is chunked
@@ -680,6 +681,7 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
 {
     // WIN = false (compile time): the tensors ARE the frame, no origin shift and no second range test
     const int fx0 = WIN ? p.src_x0 : 0, fy0 = WIN ? p.src_y0 : 0, gw = WIN ? p.gw : p.W, gh = WIN ? p.gh : p.H;
+    const int gy0 = WIN ? p.acc_y0 : 0, grows = WIN ? p.acc_h : p.H;   // rows of the frame held by G
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
     const int y0 = blockIdx.y * (4 * kPreRows) + (warp >> 1) * kPreRows;
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
     const float *cx = p.cx + (int64_t)n * p.coord_bs, *cy = p.cy + (int64_t)n * p.coord_bs;
     const uint8_t *fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
     const float *data = p.data + (int64_t)n * p.data_bs;
-    const float *Gn = G + (int64_t)n * HW * KG;
+    const float *Gn = G + (int64_t)n * grows * p.W * KG;
     const uint8_t *uno = (p.gdata && p.unocc) ? p.unocc + (int64_t)n * HW : nullptr;
     const float *go = p.gout + (int64_t)n * C * HW;
     float *gdp = p.gdata ? p.gdata + (int64_t)n * C * HW : nullptr;
@@ -736,9 +738,9 @@ __global__ void __launch_bounds__(256) splat_bwd_gather_kernel(const SplatBwdPar
             // frame but was cut away with its gradient, so it contributes nothing
             const bool bx[2] = {(unsigned)xi < (unsigned)gw, (unsigned)(xi + 1) < (unsigned)gw};
             const bool by[2] = {(unsigned)yi < (unsigned)gh, (unsigned)(yi + 1) < (unsigned)gh};
-            const int lx = xi - fx0, ly = yi - fy0;
+            const int lx = xi - fx0, ly = yi - gy0;
             const bool sx[2] = {!WIN || (unsigned)lx < (unsigned)p.W, !WIN || (unsigned)(lx + 1) < (unsigned)p.W};
-            const bool sy[2] = {!WIN || (unsigned)ly < (unsigned)p.H, !WIN || (unsigned)(ly + 1) < (unsigned)p.H};
+            const bool sy[2] = {!WIN || (unsigned)ly < (unsigned)grows, !WIN || (unsigned)(ly + 1) < (unsigned)grows};
             const float ax[2] = {__fsub_rn(__fadd_rn(x0f, 1.0f), X), __fsub_rn(X, x0f)};
             const float ay[2] = {__fsub_rn(__fadd_rn(y0f, 1.0f), Y), __fsub_rn(Y, y0f)};
             const float wx[2] = {bx[0] ? ax[0] : 0.0f, bx[1] ? ax[1] : 0.0f};      // utils.py:1110
@@ -972,7 +974,7 @@ static int splat_bwd_impl(const float *cx, const float *cy, int64_t coord_bs, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SplatBwdParams p{cx, cy, coord_bs, relative, sign, data, data_bs, flow_mask, flow_mask_bs, occlude_zero,
                      out, density, unocc, gout, gdensity, gcx, gcy, gcoord_bs, gdata, N, C, H, W,
-                     win[0], win[1], win[2], win[3]};
+                     win[0], win[1], win[2], win[3], win[0], H};
     const dim3 block(32, 8);
     const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
     SplatBwdV1 k;
@@ -1081,6 +1083,58 @@ extern "C" int ofb_splat_s_band_normalise(const float *cx, const float *cy, int6
                   occlude_zero, const_cast<float *>(acc), out, density, warped_mask, unocc, valid, valid_mode,
                   N, C, H, W, src_y0, gh, acc_y0, acc_h, nullptr, 0, W};
     k.norm<<<dim3((W + 63) / 64, (H + 4 * kNormRows - 1) / (4 * kNormRows), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, 0);
+    OFB_CHECK_LAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-band adjoint: prepass on the rank's own target rows, then (after the neighbours' halo rows of G have been
+// copied in) the gather for the rank's own sources against the extended G
+// ------------------------------------------------------------------------------------------------
+extern "C" int ofb_splat_s_kg(int C)
+{
+    SplatBwdV1 k;
+    return splat_bwd_v1(C, &k) ? k.kg : 0;
+}
+
+// G = (N, H, W, KG) floats, KG = ofb_splat_s_kg(C): per target pixel {gout_c / max(den, 1e-3), d loss / d den}
+extern "C" int ofb_splat_s_band_bwd_prepass(const float *out, const float *density, const uint8_t *unocc,
+                                            const float *gout, const float *gdensity, float *G,
+                                            int N, int C, int H, int W, void *stream)
+{
+    SplatBwdV1 k;
+    if (!density || !G || N <= 0 || C < 0 || H < 1 || W < 1 || N > 65535 || (C > 0 && (!out || !gout))) return OFB_EINVAL;
+    if (!splat_bwd_v1(C, &k)) return OFB_EINVAL;
+    SplatBwdParams p{nullptr, nullptr, 0, 1, 1.0f, nullptr, 0, nullptr, 0, 0, out, density, unocc, gout, gdensity,
+                     nullptr, nullptr, 0, nullptr, N, C, H, W, 0, 0, H, W, 0, H};
+    k.pre<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, G);
+    OFB_CHECK_LAUNCH();
+    return 0;
+}
+
+// band[4] = {src_y0, global_h, acc_y0, acc_h}: the H x W source tensors are rows [src_y0, src_y0 + H) of a field of
+// global_h rows, G stores rows [acc_y0, acc_y0 + acc_h) as (N, acc_h, W, KG).  unocc / gout are the rank's own rows.
+extern "C" int ofb_splat_s_band_bwd_gather(const float *cx, const float *cy, int64_t coord_bs, float sign,
+                                           const float *data, int64_t data_bs,
+                                           const uint8_t *flow_mask, int64_t flow_mask_bs, int occlude_zero,
+                                           const float *G, const uint8_t *unocc, const float *gout,
+                                           float *gcx, float *gcy, int64_t gcoord_bs, float *gdata,
+                                           int N, int C, int H, int W, const int *band, void *stream)
+{
+    SplatBwdV1 k;
+    if (!cx || !cy || !G || !band || N <= 0 || C < 0 || H < 1 || W < 1 || N > 65535 || (C > 0 && !data)) return OFB_EINVAL;
+    if ((gcx == nullptr) != (gcy == nullptr)) return OFB_EINVAL;
+    if (gdata && unocc && !gout) return OFB_EINVAL;
+    if (!splat_bwd_v1(C, &k)) return OFB_EINVAL;
+    const int src_y0 = band[0], gh = band[1], acc_y0 = band[2], acc_h = band[3];
+    if (src_y0 < 0 || src_y0 + H > gh || acc_y0 < 0 || acc_h < 1 || acc_y0 + acc_h > gh ||
+        (int64_t)acc_h * W > 0x3fffffff)
+        return OFB_EINVAL;
+    if (!gcx && !gdata) return 0;
+    SplatBwdParams p{cx, cy, coord_bs, 1, sign, data, data_bs, flow_mask, flow_mask_bs, occlude_zero,
+                     nullptr, nullptr, unocc, gout, nullptr, gcx, gcy, gcoord_bs, gdata, N, C, H, W,
+                     src_y0, 0, gh, W, acc_y0, acc_h};
+    k.gat_win<<<dim3((W + 63) / 64, (H + 4 * kPreRows - 1) / (4 * kPreRows), N), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, G);
     OFB_CHECK_LAUNCH();
     return 0;
 }

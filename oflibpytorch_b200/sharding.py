@@ -154,7 +154,9 @@ def apply_s_rowbands(flow_band: torch.Tensor, payload_band: torch.Tensor, *, h_t
     of `apply_t_rowbands`, i.e. `Flow(flow,'s',mask).apply(payload, payload_mask, return_valid_area=True)` for a field
     that does not fit one GPU.  Every rank splats its source rows into a local accumulator extended by `halo` rows on
     both sides, the halos are exchanged with the two neighbours (P2P over NVLink) and added in a fixed order, and each
-    rank normalises its own rows.  Forward only.  `halo` defaults to ceil(max |flow_y|) + 2 over all ranks.
+    rank normalises its own rows.  Differentiable with respect to the flow and the payload (the backward pass exchanges
+    halo rows with the neighbours too, so every rank has to run it).  `halo` defaults to ceil(max |flow_y|) + 2 over
+    all ranks.
     Returns (out_band (N,C,hb,W), valid_band (N,hb,W) or None)."""
     import math
     import torch.distributed as dist
@@ -181,12 +183,50 @@ def apply_s_rowbands(flow_band: torch.Tensor, payload_band: torch.Tensor, *, h_t
     else:
         dm = None
     flow_mask_used = fm if consider_mask else None
-    band = (a, h_total, lo, hi - lo)
-    acc = _ops.splat_band_accumulate(flow_band, payload_band, dm, flow_mask_used, 1.0, True, band)
-    own = exchange_add_accumulator_halos(acc, a - lo, hi - b, rank, world_size, group)
-    out, valid = _ops.splat_band_normalise(own, flow_band, payload_band, dm, flow_mask_used, True,
-                                           _ops.VALID_GT if want_valid else _ops.VALID_NONE, (a, h_total, a, hb))
+    out, valid = _SplatRowBands.apply(flow_band, payload_band, dm, flow_mask_used, (a, b, h_total, lo, hi, halo),
+                                      rank, world_size, want_valid, group)
     return out, (valid if want_valid else None)
+
+
+class _SplatRowBands(torch.autograd.Function):
+    """Row-band splat with its adjoint.  Forward: accumulate own sources into the halo-extended accumulator, add the
+    neighbours' halos, normalise own rows.  Backward: per-target prepass on own rows, COPY the neighbours' halo rows
+    of it in, gather for own sources.  Both directions exchange with the two neighbours, so every rank must run the
+    backward pass (an absent upstream gradient counts as zero)."""
+
+    @staticmethod
+    def forward(ctx, flow_band, payload_band, dm, flow_mask_used, geom, rank, world_size, want_valid, group):
+        from . import _ops
+        a, b, h_total, lo, hi, halo = geom
+        hb = b - a
+        acc = _ops.splat_band_accumulate(flow_band, payload_band, dm, flow_mask_used, 1.0, True, (a, h_total, lo, hi - lo))
+        own = exchange_add_accumulator_halos(acc, a - lo, hi - b, rank, world_size, group)
+        out, valid, density, unocc = _ops.splat_band_normalise(
+            own, flow_band, payload_band, dm, flow_mask_used, True,
+            _ops.VALID_GT if want_valid else _ops.VALID_NONE, (a, h_total, a, hb), want_aux=True)
+        ctx.save_for_backward(flow_band, payload_band, flow_mask_used, out, density, unocc)
+        ctx.geom, ctx.rank, ctx.world_size, ctx.group = geom, rank, world_size, group
+        ctx.mark_non_differentiable(valid)
+        ctx.set_materialize_grads(False)
+        return out, valid
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout, _gvalid):
+        from . import _ops
+        flow_band, payload_band, flow_mask_used, out, density, unocc = ctx.saved_tensors
+        a, b, h_total, lo, hi, halo = ctx.geom
+        need_gflow, need_gdata = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if gout is None:
+            gout = torch.zeros_like(out)
+        g = _ops.splat_band_bwd_prepass(out, density, unocc, gout)                  # (N, hb, W, KG), own rows
+        n, hb, w, kg = g.shape
+        g_ext, k_top = exchange_row_halos(g.view(n, hb, w * kg), halo, ctx.rank, ctx.world_size, ctx.group)
+        acc_h = g_ext.shape[-2]
+        gflow, gdata = _ops.splat_band_bwd_gather(flow_band, payload_band, flow_mask_used, True,
+                                                  g_ext.reshape(n, acc_h, w, kg), unocc, gout,
+                                                  (a, h_total, a - k_top, acc_h), need_gflow, need_gdata)
+        return (gflow if need_gflow else None), (gdata if need_gdata else None), None, None, None, None, None, None, None
 
 
 def gather_shards(local: torch.Tensor, group=None) -> List[torch.Tensor]:

@@ -251,6 +251,61 @@ def test_row_band_splat_equals_rows_of_the_full_splat():
         assert_mask_equal(valid, vfull[:, a:b], 'band valid')
 
 
+def test_row_band_splat_adjoint_equals_rows_of_the_full_gradient():
+    """Row-band splat adjoint (ofb_splat_s_band_bwd_prepass / _gather): per-band prepass, halo rows of G copied in from
+    the neighbouring bands, gather for the band's own sources -- reproduces the rows of the full-field gradients
+    (single GPU emulation of the multi-GPU scheme).  Also the public wrapper with world_size = 1 under autograd."""
+    from oflibpytorch_b200 import _ops, sharding
+    n, c, h, w = 2, 3, 90, 72
+    flow = smooth_flow(n, h, w, 4.0, 996)
+    flow[:, :, 30:40, 10:30] = 0.0
+    img = torch.rand(n, c, h, w, generator=gen(997))
+    gout = torch.rand(n, c, h, w, generator=gen(998))
+    fmask, tmask = holed_mask(n, h, w, 999), holed_mask(n, h, w, 1000)
+    fg, ig = flow.cuda().requires_grad_(), img.cuda().requires_grad_()
+    full, vfull = of().Flow(fg, 's', fmask.cuda()).apply(ig, tmask.cuda(), return_valid_area=True)
+    full.backward(gout.cuda())
+    # forward pieces of the full field that the bands would hold (out, density, unocc) via the band API itself
+    k = int(flow[:, 1].abs().max().ceil()) + 2
+    bands = [(0, 35), (35, 61), (61, 90)]
+    dm = (tmask & fmask).cuda()
+    fl, im, fm, go = flow.cuda(), img.cuda(), fmask.cuda(), gout.cuda()
+    accs = []
+    for a, b in bands:
+        lo, hi = max(a - k, 0), min(b + k, h)
+        accs.append((lo, hi, _ops.splat_band_accumulate(fl[:, :, a:b].contiguous(), im[:, :, a:b].contiguous(),
+                                                         dm[:, a:b].contiguous(), fm[:, a:b].contiguous(), 1.0, True,
+                                                         (a, h, lo, hi - lo))))
+    total = torch.zeros((n, h, w, accs[0][2].shape[-1]), device='cuda')
+    for lo, hi, acc in accs:
+        total[:, lo:hi] += acc
+    gs, aux = [], []
+    for a, b in bands:
+        out, valid, den, unocc = _ops.splat_band_normalise(total[:, a:b].contiguous(), fl[:, :, a:b].contiguous(),
+                                                           im[:, :, a:b].contiguous(), dm[:, a:b].contiguous(),
+                                                           fm[:, a:b].contiguous(), True, _ops.VALID_GT, (a, h, a, b - a),
+                                                           want_aux=True)
+        aux.append(unocc)
+        gs.append(_ops.splat_band_bwd_prepass(out, den, unocc, go[:, :, a:b].contiguous()))
+    g_full = torch.cat(gs, dim=1)                                           # what the halo exchange assembles
+    for (a, b), unocc in zip(bands, aux):
+        lo, hi = max(a - k, 0), min(b + k, h)
+        gflow, gdata = _ops.splat_band_bwd_gather(fl[:, :, a:b].contiguous(), im[:, :, a:b].contiguous(),
+                                                  fm[:, a:b].contiguous(), True, g_full[:, lo:hi].contiguous(), unocc,
+                                                  go[:, :, a:b].contiguous(), (a, h, lo, hi - lo), True, True)
+        assert_grad_close(gflow, fg.grad[:, :, a:b], 'band gflow')
+        assert_grad_close(gdata, ig.grad[:, :, a:b], 'band gdata')
+    # the public wrapper as a single band: autograd through accumulate / normalise / prepass / gather
+    f1, i1 = flow.cuda().requires_grad_(), img.cuda().requires_grad_()
+    o1, v1 = sharding.apply_s_rowbands(f1, i1, h_total=h, rank=0, world_size=1, flow_mask_band=fm,
+                                       payload_mask_band=tmask.cuda())
+    o1.backward(go)
+    assert_close(o1, full, 'single-band out')
+    assert_mask_equal(v1, vfull, 'single-band valid')
+    assert_grad_close(f1.grad, fg.grad, 'single-band gflow')
+    assert_grad_close(i1.grad, ig.grad, 'single-band gdata')
+
+
 def test_chained_combine_apply_backward_matches_oracle():
     """BASELINE.json config 5 at test scale: acc = acc.combine_with(f_i, 3); img_i = acc.apply(img, valid area);
     loss = sum_i <g_i, img_i>; ONE backward through the whole chain -> gradients of every frame's flow and of the image."""
