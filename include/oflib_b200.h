@@ -53,6 +53,12 @@ const char *ofb_error_string(int status);
 int64_t ofb_launch_count(void);
 void ofb_launch_count_reset(void);
 
+/* Tuning knobs for profiling sweeps (the defaults are the measured best; not needed in production).
+ *   key 1  W adjoint implementation: -1 auto, 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA reduce flush
+ *   key 2  W adjoint ring: output rows per warp task
+ * Returns 0, or OFB_EINVAL for an unknown key.  Process-wide, not thread-safe. */
+int ofb_set_option(int key, int value);
+
 /* Self-test: counts the float bit patterns b in [lo_bits, hi_bits) (both signs) for which the kernels' coordinate
  * round trip (constant-reciprocal division, d = W-1 or H-1) differs from the one evaluated with IEEE division as
  * the reference does (utils.py:462-465 + ATen GridSampler.h:31).  *mismatches (device, zeroed by the caller) must

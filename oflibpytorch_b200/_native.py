@@ -22,6 +22,7 @@ SIGNATURES = {
     'ofb_error_string': ([_I], ctypes.c_char_p),
     'ofb_launch_count': ([], _L),
     'ofb_launch_count_reset': ([], None),
+    'ofb_set_option': ([_I, _I], _I),
     'ofb_selftest_div': ([_F, ctypes.c_uint32, ctypes.c_uint32, _P, _P], _I),
     'ofb_flow_stats': ([_P, _P, _P, _I, _I, _I, _P], _I),
     'ofb_warp_t_fwd': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P], _I),
