@@ -163,36 +163,68 @@ def gpu_step(of, flow, img, mask, tmask, gout):
     return out, valid, gf, gi
 
 
-def secondary_workloads(of, dev, peak):
-    """BASELINE.json configs 3 and 4 through the public API, CUDA events, device-resident inputs.  Reported under
-    `other_workloads` for information; the bench line proper is config 2.  frac = algorithmic bytes
-    / time / measured HBM peak."""
-    def timeit(fn, steps=5, warm=2):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps
+def _timeit(fn, steps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
-    def entry(ms, px, bytes_per_px):
-        return {'ms': round(ms, 3), 'Mpix/s': round(px / ms / 1e3, 1),
-                'frac_of_hbm': round(bytes_per_px * px / (ms * 1e-3) / 1e9 / peak, 3), 'bytes_per_px': bytes_per_px}
 
+def _entry(ms, px, bytes_per_px, peak):
+    return {'ms': round(ms, 3), 'Mpix/s': round(px / ms / 1e3, 1), 'bytes_per_px': bytes_per_px,
+            'algorithmic_GB': round(bytes_per_px * px / 1e9, 3),
+            'frac_of_hbm': round(bytes_per_px * px / (ms * 1e-3) / 1e9 / peak, 3)}
+
+
+def holed(n, h, w, dev, scale=1):
+    m = torch.ones(n, h, w, dtype=torch.bool, device=dev)
+    m[:, 300 * scale:500 * scale, 700 * scale:1100 * scale] = False
+    m[:, :, ::97] = False
+    return m
+
+
+def workload_combine_1080p(of, dev, peak, n=64):
+    """The other half of BASELINE.json's metric: of.combine_flows forward + backward at 64 x 1080p (tensor API,
+    reference flow_operations.py:84-188): mode 3 for both references (one fused W launch) and mode 2 for ref 's'
+    (splat-backed: S(v1, v2 - v1), reference flow_class.py:1768).  Bytes per pixel: SURVEY.md 8(d)."""
     res = {}
-    n = 32
+    fa, fb = smooth_flow(n, H, W, 8.0, 20, dev), smooth_flow(n, H, W, 8.0, 21, dev)
+    g = torch.Generator(device=dev).manual_seed(22)
+    gout = torch.rand(n, 2, H, W, generator=g, device=dev)
+    px = n * H * W
+
+    def make(mode, ref):
+        def fn():
+            a = fa.detach().requires_grad_()
+            b = fb.detach().requires_grad_()
+            out = of.combine_flows(a, b, mode, ref)
+            out.backward(gout)
+        return fn
+
+    # tensor API: all-true masks, so mode 3 moves 8+8 -> 8 forward and 8+8+8 -> 8+8 backward = 24 + 40
+    res['combine_flows mode 3 ref t, fwd+bwd, %dx1080x1920' % n] = _entry(_timeit(make(3, 't')), px, 24 + 40, peak)
+    res['combine_flows mode 3 ref s, fwd+bwd, %dx1080x1920' % n] = _entry(_timeit(make(3, 's')), px, 24 + 40, peak)
+    # mode 2 ref 's': one subtraction (24) + S with a 2-channel payload, fwd 8+8 -> 8 and bwd per SURVEY 8(d) 16C+21 = 53
+    res['combine_flows mode 2 ref s (splat-backed), fwd+bwd, %dx1080x1920' % n] = _entry(
+        _timeit(make(2, 's')), px, 24 + 24 + 53 + 24, peak)
+    return res
+
+
+def workload_cfg3(of, dev, peak, n=32):
+    """BASELINE.json configs[2]: forward 's' warp through the splat, 1080p batch 32, with validity; fwd and fwd+bwd."""
+    res = {}
     flow = smooth_flow(n, H, W, 8.0, 5, dev)
-    flow[:, :, 200:440, 300:700] = 0.0
+    flow[:, :, 200:440, 300:700] = 0.0          # 5 % of the pixels exactly zero: the occlusion rule
     g = torch.Generator(device=dev).manual_seed(6)
     img = torch.rand(n, C, H, W, generator=g, device=dev)
     gout = torch.rand(n, C, H, W, generator=g, device=dev)
-    mask = torch.ones(n, H, W, dtype=torch.bool, device=dev)
-    mask[:, 300:500, 700:1100] = False
-    mask[:, :, ::97] = False
+    mask = holed(n, H, W, dev)
     tmask = mask.roll(131, dims=2)
     px = n * H * W
 
@@ -206,15 +238,17 @@ def secondary_workloads(of, dev, peak):
         o, _v = of.Flow(f, 's', mask).apply(i, tmask, return_valid_area=True)
         o.backward(gout)
 
-    res['cfg3 Flow.apply s + valid area, 32x3x1080x1920, fwd'] = entry(timeit(s_fwd), px, 35)
-    res['cfg3 Flow.apply s + valid area, 32x3x1080x1920, fwd+bwd'] = entry(timeit(s_fwdbwd), px, 35 + 69)
-    del flow, img, gout, mask, tmask
-    torch.cuda.empty_cache()
-    n, hh, ww = 16, 2160, 3840
+    res['cfg3 Flow.apply s + valid area, fwd, %dx3x1080x1920' % n] = _entry(_timeit(s_fwd), px, 35, peak)
+    res['cfg3 Flow.apply s + valid area, fwd+bwd, %dx3x1080x1920' % n] = _entry(_timeit(s_fwdbwd), px, 35 + 69, peak)
+    return res
+
+
+def workload_cfg4(of, dev, peak, n=16):
+    """BASELINE.json configs[3]: combine mode 3 + switch_ref on 4K batch 16 with masks, both references."""
+    res = {}
+    hh, ww = 2160, 3840
     fa, fb = smooth_flow(n, hh, ww, 8.0, 8, dev), smooth_flow(n, hh, ww, 8.0, 9, dev)
-    m = torch.ones(n, hh, ww, dtype=torch.bool, device=dev)
-    m[:, 600:1000, 1400:2200] = False
-    m[:, :, ::97] = False
+    m = holed(n, hh, ww, dev, 2)
     px = n * hh * ww
     for ref in 'ts':
         a, b = of.Flow(fa, ref, m), of.Flow(fb, ref, m)
@@ -227,9 +261,46 @@ def secondary_workloads(of, dev, peak):
             with torch.no_grad():
                 return a.switch_ref()
 
-        res['cfg4 combine_with mode 3 ref %s, 16x2160x3840, masked' % ref] = entry(timeit(comb), px, 27)
-        res['cfg4 switch_ref from %s, 16x2160x3840, masked' % ref] = entry(timeit(sw), px, 18)
+        def both():
+            with torch.no_grad():
+                return a.combine_with(b, 3).switch_ref()
+
+        res['cfg4 combine_with mode 3 ref %s, %dx2160x3840, masked' % (ref, n)] = _entry(_timeit(comb), px, 27, peak)
+        res['cfg4 switch_ref from %s, %dx2160x3840, masked' % (ref, n)] = _entry(_timeit(sw), px, 18, peak)
+        res['cfg4 combine_with mode 3 then switch_ref, ref %s, %dx2160x3840' % (ref, n)] = _entry(
+            _timeit(both), px, 27 + 18, peak)
     return res
+
+
+CHAIN_FRAMES = 256
+
+
+def workload_cfg5(of, dev, peak, rank, world, frames_total=CHAIN_FRAMES, steps=2):
+    """BASELINE.json configs[4], STRONG scaling: 256 frames of 4K flow (seeds 100..355, sigma 4 px), chained
+    acc = acc.combine_with(f_i, 3); img_i = acc.apply(img, return_valid_area=True); loss = sum_i img_i.sum(); one
+    backward through the chain (reference flow_class.py:1648-1810 + :755-959).  Rank g of G owns frames
+    [256 g / G, 256 (g+1) / G) and chains them among themselves; no collective on the data path.
+    Returns this rank's ms per chain; the caller takes the max over ranks."""
+    hh, ww = 2160, 3840
+    lo, hi = frames_total * rank // world, frames_total * (rank + 1) // world
+    flows = [smooth_flow(1, hh, ww, 4.0, 100 + i, dev) for i in range(lo, hi)]
+    g = torch.Generator(device=dev).manual_seed(7)
+    img = torch.rand(1, C, hh, ww, generator=g, device=dev)
+
+    def chain():
+        fl = [f.detach().requires_grad_() for f in flows]
+        im = img.detach().requires_grad_()
+        acc, loss = None, None
+        for f in fl:
+            cur = of.Flow(f, 't')
+            acc = cur if acc is None else acc.combine_with(cur, 3)
+            out, _valid = acc.apply(im, return_valid_area=True)
+            loss = out.sum() if loss is None else loss + out.sum()
+        loss.backward()
+
+    ms = _timeit(chain, steps=steps, warm=1)
+    del flows
+    return ms, hi - lo
 
 
 def main():
@@ -243,7 +314,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-chunk', type=int, default=8, help='batch items per pipelined chunk of the e2e path')
-    ap.add_argument('--extra', action='store_true', help='also time BASELINE.json configs 3 and 4 (information only)')
+    ap.add_argument('--no-workloads', action='store_true', help='skip combine_flows and configs 3, 4, 5')
+    ap.add_argument('--chain-frames', type=int, default=CHAIN_FRAMES, help='frames of the config-5 chain (256 = the named config)')
     ap.add_argument('--sigma', type=float, default=8.0, help='flow magnitude (px) of the synthetic field; 8 = the named config')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else max(args.warmup, 1)
@@ -396,12 +468,33 @@ def main():
                       'H2D/compute/D2H on three streams' % args.e2e_chunk}
         del host_in, host_out
 
-    # ---------------------------------------------------------------- secondary workloads (information only)
-    extra = None
-    if rank == 0 and world == 1 and args.extra:
+    # ---------------------------------------------------------------- the rest of BASELINE.json's metric and configs
+    # combine_flows fwd+bwd at 64 x 1080p, configs 3 and 4 (rank 0, N = 1), and config 5 as STRONG scaling over all
+    # ranks: 256 frames of 4K sharded [256 g / G, 256 (g+1) / G), time = max over ranks.
+    workloads = None
+    if not args.no_workloads:
         del flow, img, mask, tmask, gout
         torch.cuda.empty_cache()
-        extra = secondary_workloads(of, dev, peak)
+        workloads = {}
+        if world == 1:
+            workloads.update(workload_combine_1080p(of, dev, peak))
+            torch.cuda.empty_cache()
+            workloads.update(workload_cfg3(of, dev, peak))
+            torch.cuda.empty_cache()
+            workloads.update(workload_cfg4(of, dev, peak))
+            torch.cuda.empty_cache()
+        barrier()
+        ms5, mine = workload_cfg5(of, dev, peak, rank, world, args.chain_frames)
+        t5 = torch.tensor([ms5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        ms5 = float(t5.item())
+        px5 = args.chain_frames * 2160 * 3840
+        e5 = _entry(ms5, px5, 155, peak * world)
+        e5.update({'frames_total': args.chain_frames, 'frames_per_rank': mine, 'n_gpus': world, 'scaling': 'strong',
+                   'what': 'acc = acc.combine_with(f_i, 3); acc.apply(img, return_valid_area=True); one backward '
+                           'through the chain; time = max over ranks; frac is of n_gpus x the HBM peak'})
+        workloads['cfg5 chained combine+apply fwd+bwd, %d frames of 2160x3840, strong scaling' % args.chain_frames] = e5
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
@@ -421,7 +514,7 @@ def main():
                        'l2': 'inputs (%.1f GB per step) exceed the 126 MB L2; no flush needed' % (
                            (BYTES_PER_PX['ofb_warp_t_fwd'] + BYTES_PER_PX['ofb_warp_t_bwd']) * px / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
-            'other_workloads': extra,
+            'workloads': workloads,
         }
         print(json.dumps(line))
     if world > 1:

@@ -3,7 +3,7 @@
 # --set full capture of the three kernels of the step and of the splat kernels.  Outputs under gpurun_out/.
 set -x
 mkdir -p gpurun_out
-python bench.py --extra > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 tail -c 600 gpurun_out/bench_final.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_final.csv \
     python bench.py --steps 5 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
