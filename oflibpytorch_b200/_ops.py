@@ -552,9 +552,10 @@ def splat_band_normalise(acc, flow, data, data_mask, flow_mask, occlude_zero, va
         density = torch.empty((n, h, w) if want_aux else (0,), dtype=torch.float32, device=flow.device)
         unocc = torch.empty((n, h, w) if (want_aux and occlude_zero) else (0,), dtype=torch.bool, device=flow.device)
         cx, cy = flow[:, 0], flow[:, 1]
+        acc = acc.contiguous()                 # bound to a name: the pointer must outlive the launch
         _call("ofb_splat_s_band_normalise", _p(cx), _p(cy), 0 if (flow.shape[0] == 1 and n > 1) else 2 * hw, 1,
               _p(data) if c else None, _bs(data, n, c * hw), _p(data_mask), _bs(data_mask, n, hw),
-              _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(acc.contiguous()), _p(out) if c else None,
+              _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(acc), _p(out) if c else None,
               _p(density) if want_aux else None, None, _p(unocc) if (want_aux and occlude_zero) else None,
               _p(valid) if want_valid else None, valid_mode, n, c, h, w,
               (ctypes.c_int * 4)(*[int(v) for v in band]), _stream())
@@ -577,7 +578,8 @@ def splat_band_bwd_prepass(out, density, unocc, gout):
     return g
 
 
-def splat_band_bwd_gather(flow, data, flow_mask, occlude_zero, g_ext, unocc, gout, band, need_gflow, need_gdata):
+def splat_band_bwd_gather(flow, data, flow_mask, occlude_zero, g_ext, unocc, gout, band, need_gflow, need_gdata,
+                          sign=1.0):
     """Row-band splat adjoint, step 3: gradients of this rank's own sources against the halo-extended G
     (ofb_splat_s_band_bwd_gather).  band = (src_y0, global_h, acc_y0, acc_h).  Returns (gflow, gdata)."""
     flow, data, gout = _f32c(flow.detach()), _f32c(data.detach()), _f32c(gout)
@@ -589,8 +591,9 @@ def splat_band_bwd_gather(flow, data, flow_mask, occlude_zero, g_ext, unocc, gou
         gdata = torch.empty((n, c, h, w) if need_gdata else (0,), dtype=torch.float32, device=flow.device)
         gcx = ctypes.c_void_p(gflow.data_ptr()) if need_gflow else None
         gcy = ctypes.c_void_p(gflow.data_ptr() + 4 * hw) if need_gflow else None
-        _call("ofb_splat_s_band_bwd_gather", _p(flow[:, 0]), _p(flow[:, 1]), 2 * hw, 1.0, _p(data), c * hw,
-              _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(g_ext.contiguous()),
+        g_ext = g_ext.contiguous()             # bound to a name: the pointer must outlive the launch
+        _call("ofb_splat_s_band_bwd_gather", _p(flow[:, 0]), _p(flow[:, 1]), 2 * hw, float(sign), _p(data), c * hw,
+              _p(flow_mask), _bs(flow_mask, n, hw), int(occlude_zero), _p(g_ext),
               _p(unocc) if (unocc is not None and unocc.numel()) else None, _p(gout), gcx, gcy, 2 * hw,
               _p(gdata) if need_gdata else None, n, c, h, w, (ctypes.c_int * 4)(*[int(v) for v in band]), _stream())
     return gflow, gdata
@@ -635,6 +638,9 @@ def _flo_to_planar(interleaved):
 
 def _kitti_decode(png_bgr, want_valid):
     require_cuda(png_bgr, "KITTI data")
+    if png_bgr.dtype not in (torch.int16, torch.uint16) or png_bgr.dim() != 4 or png_bgr.shape[-1] != 3:
+        raise TypeError("oflibpytorch_b200: KITTI data must be an (N,H,W,3) 16-bit tensor, got %s %s"
+                        % (png_bgr.dtype, tuple(png_bgr.shape)))
     x = png_bgr.contiguous()
     n, h, w, _ = x.shape
     with torch.cuda.device(x.device):

@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 namespace ofb {
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 }
 
 extern "C" int ofb_abi_version(void) { return OFB_ABI_VERSION; }
@@ -16,5 +16,5 @@ extern "C" const char *ofb_error_string(int status)
     return "oflib_b200: unknown error";
 }
 
-extern "C" int64_t ofb_launch_count(void) { return ofb::g_launches; }
+extern "C" int64_t ofb_launch_count(void) { return ofb::g_launches.load(); }
 extern "C" void ofb_launch_count_reset(void) { ofb::g_launches = 0; }

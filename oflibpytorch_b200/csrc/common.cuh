@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/oflib_b200.h"
 
 #define OFB_THRESHOLD 1e-3f     // utils.py:23
@@ -15,7 +17,7 @@
 
 namespace ofb {
 
-extern int64_t g_launches;   // host-side launch counter (api.cu)
+extern std::atomic<int64_t> g_launches;   // host-side launch counter (api.cu)
 
 // pixel -> normalised [-1,1] (utils.py:462-465) -> pixel (ATen GridSampler.h:31), in fp32
 __device__ __forceinline__ float round_trip(float c, float size_m1)

@@ -107,6 +107,8 @@ class Flow(object):
             if getattr(self, '_stats_unmasked', None) is not None:
                 # all-true mask: masked bits == unmasked bits
                 self._stats = [fl | ((fl & 2) << 2) | ((fl & 4) << 2) for fl in self._stats_unmasked]
+            else:
+                self._stats = None      # flags cached against the previous mask are stale: recomputed lazily
         else:
             m = get_valid_mask(input_mask, desired_shape=self.shape, error_string="Error setting flow mask: ")
             self._mask = m.to(self._vecs.device)
@@ -182,13 +184,20 @@ class Flow(object):
             raise ValueError(err_a)
         return ov.to(self._device), (None if om is None else om.to(self._device))
 
+    def _broadcast_mask(self, om: Optional[torch.Tensor], n_other: int) -> torch.Tensor:
+        """Mask of self (+/-) other: the AND of both masks, expanded to the broadcast batch size so that vectors and
+        mask of the result always agree (the reference gets there through the Flow constructor, flow_class.py:476)."""
+        m = self._mask if om is None else (self._mask & om)
+        n = max(self.shape[0], n_other)
+        return m if m.shape[0] == n else m.expand(n, -1, -1).contiguous()
+
     def __add__(self, other) -> FlowAlias:
         ov, om = self._other_operand(other, "adding to", "Addend",
                                      "Error adding to flow: Augend and addend batch dimensions don't match, "
                                      "and neither is 1")
         if self.shape[1:] != tuple(ov.shape[2:]):
             raise ValueError("Error adding to flow: Augend and addend flow objects are not the same shape")
-        return Flow._make(self._vecs + ov, self._ref, self._mask if om is None else (self._mask & om))
+        return Flow._make(self._vecs + ov, self._ref, self._broadcast_mask(om, ov.shape[0]))
 
     def __sub__(self, other) -> FlowAlias:
         ov, om = self._other_operand(other, "subtracting from", "Subtrahend",
@@ -196,7 +205,7 @@ class Flow(object):
                                      "match, and neither is 1")
         if self.shape[1:] != tuple(ov.shape[2:]):
             raise ValueError("Error subtracting from flow: Minuend and subtrahend flow objects are not the same shape")
-        return Flow._make(self._vecs - ov, self._ref, self._mask if om is None else (self._mask & om))
+        return Flow._make(self._vecs - ov, self._ref, self._broadcast_mask(om, ov.shape[0]))
 
     def _scalar_like(self, other, verb: str, noun: str):
         """Shared operand handling of __mul__/__truediv__/__pow__ (flow_class.py:533-678)."""

@@ -170,8 +170,20 @@ def apply_s_rowbands(flow_band: torch.Tensor, payload_band: torch.Tensor, *, h_t
         if dist.is_available() and dist.is_initialized() and world_size > 1:
             dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
         halo = int(math.ceil(float(k.item()))) + 2
-    if world_size > 1 and halo > hb:
-        raise ValueError("halo of %d rows exceeds this rank's band of %d rows; use fewer ranks" % (halo, hb))
+    # every rank must take the same decision (bands differ by one row): test against the smallest band
+    if world_size > 1 and halo > h_total // world_size:
+        raise ValueError("halo of %d rows exceeds the smallest band of %d rows; use fewer ranks"
+                         % (halo, h_total // world_size))
+    # apply_flow's early-out (utils.py:497-498) looks at the WHOLE field: agree on it across the bands
+    local_zero = bool((flow_band.detach().abs() < 1e-3).all().item())
+    if agree_all_zero(local_zero, group):
+        valid = None
+        if want_valid:
+            valid = payload_mask_band if payload_mask_band is not None else torch.ones(
+                (payload_band.shape[0], hb, w), dtype=torch.bool, device=payload_band.device)
+            if flow_mask_band is not None:                           # flow_class.py:880-895
+                valid = valid & flow_mask_band
+        return payload_band, valid
     lo, hi = max(a - halo, 0), min(b + halo, h_total)
     fm = flow_mask_band
     dm = payload_mask_band

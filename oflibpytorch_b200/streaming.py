@@ -91,15 +91,23 @@ class HostWarpPipeline:
                     i, None if d_tmask is None else d_tmask[:m], return_valid_area=True)
                 gf = gi = None
                 if want_grad:
-                    gf, gi = torch.autograd.grad(out, (f, i), d_gout[:m])
+                    # an all-zero chunk takes apply's early-out: `out` is the input image, the flow is unused
+                    gf, gi = torch.autograd.grad(out, (f, i), d_gout[:m], allow_unused=True)
+                    gf = torch.zeros_like(f) if gf is None else gf
+                    gi = torch.zeros_like(i) if gi is None else gi
                 done = torch.cuda.Event()
                 done.record(compute)
-                free[k % 2] = done
                 with torch.cuda.stream(self.s_d2h):
                     self.s_d2h.wait_event(done)
                     for dst, src in ((out_h, out), (valid_h, valid), (gflow_h, gf), (gimg_h, gi)):
                         if src is not None:
                             src.record_stream(self.s_d2h)
                             dst[a:b].copy_(src.detach(), non_blocking=True)
+                    # the early-out can hand back views of this chunk's input buffers: they may only be overwritten
+                    # by the upload of chunk k+2 once the copies above have read them
+                    drained = torch.cuda.Event()
+                    drained.record(self.s_d2h)
+                free[k % 2] = drained
             compute.wait_stream(self.s_d2h)
+            self.s_d2h.synchronize()            # the returned host tensors are complete when run() returns
         return out_h, valid_h, gflow_h, gimg_h
