@@ -41,6 +41,7 @@ BYTES_PER_PX = {  # algorithmic bytes per flow pixel, SURVEY.md section 8(d), C 
     'ofb_warp_t_fwd': 8 * C + 10 + 1,      # flow 8 + payload 4C + 2 masks -> out 4C + valid 1      = 35
     'ofb_warp_t_bwd': 12 * C + 16,         # gout 4C + flow 8 + payload 4C -> gflow 8 + gpayload 4C = 52
     'ofb_flow_stats': 8 + 1,               # flow 8 + mask 1
+    'ofb_flow_stats_batch': 8 + 1,
 }
 
 
@@ -299,8 +300,44 @@ def workload_cfg5(of, dev, peak, rank, world, frames_total=CHAIN_FRAMES, steps=2
         loss.backward()
 
     ms = _timeit(chain, steps=steps, warm=1)
+    of.check_deferred()
+
+    # The same chain captured ONCE into a CUDA graph (forward and backward; possible because 'deferred' validation
+    # leaves no host read inside) and replayed: every kernel runs again on every replay, only the Python / autograd
+    # dispatch is gone.  Reported beside the eager number, never instead of it.
+    ms_graph = None
+    if of.get_validation() == 'deferred':
+        try:
+            fl = [f.detach().requires_grad_() for f in flows]
+            im = img.detach().requires_grad_()
+
+            def body():
+                acc, loss = None, None
+                for f in fl:
+                    cur = of.Flow(f, 't')
+                    acc = cur if acc is None else acc.combine_with(cur, 3)
+                    out, _valid = acc.apply(im, return_valid_area=True)
+                    loss = out.sum() if loss is None else loss + out.sum()
+                loss.backward()
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            for t in fl + [im]:
+                t.grad = None
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            ms_graph = _timeit(graph.replay, steps=steps + 1, warm=1)
+            of.check_deferred()
+            del graph, fl, im
+        except Exception as exc:        # noqa: BLE001 -- the eager number stands on its own
+            ms_graph = 'capture failed: %s' % str(exc)[:120]
+            torch.cuda.synchronize()
     del flows
-    return ms, hi - lo
+    return ms, hi - lo, ms_graph
 
 
 def main():
@@ -314,6 +351,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--e2e-chunk', type=int, default=8, help='batch items per pipelined chunk of the e2e path')
+    ap.add_argument('--validation', default='deferred', choices=['eager', 'deferred'],
+                    help="flow validation mode of the package (eager = one host read per user flow, the reference's contract)")
     ap.add_argument('--no-workloads', action='store_true', help='skip combine_flows and configs 3, 4, 5')
     ap.add_argument('--chain-frames', type=int, default=CHAIN_FRAMES, help='frames of the config-5 chain (256 = the named config)')
     ap.add_argument('--sigma', type=float, default=8.0, help='flow magnitude (px) of the synthetic field; 8 = the named config')
@@ -350,6 +389,10 @@ def main():
     from oflibpytorch_b200 import _native, _ops
     import torch.distributed as dist
 
+    # 'deferred' validation (the opt-out of the per-flow host read, oflibpytorch_b200/utils.py): the finite test and
+    # the reference's zero-flow early-outs are evaluated on the device; the deferred finite test is read back once
+    # after each timed loop.  Results are identical to 'eager' (tests/test_gpu_deferred.py).
+    of.set_validation(args.validation)
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -380,6 +423,7 @@ def main():
         gpu_step(of, flow, img, mask, tmask, gout)
     e1.record()
     barrier()
+    of.check_deferred()
     clocks = sampler.stop() if rank == 0 else None
     launches = _native.launch_count()
     prof, _ops.PROFILE = _ops.PROFILE, None
@@ -391,7 +435,7 @@ def main():
 
     per_kernel = {}
     for name, a, b in prof:
-        per_kernel.setdefault(name, []).append(a.elapsed_time(b))
+        per_kernel.setdefault(name[:-3] if name.endswith('_ex') else name, []).append(a.elapsed_time(b))
     peak, peak_src = measured_peak()
     kernels = {}
     for name, ts in per_kernel.items():
@@ -484,13 +528,20 @@ def main():
             workloads.update(workload_cfg4(of, dev, peak))
             torch.cuda.empty_cache()
         barrier()
-        ms5, mine = workload_cfg5(of, dev, peak, rank, world, args.chain_frames)
-        t5 = torch.tensor([ms5], dtype=torch.float64, device=dev)
+        ms5, mine, ms5g = workload_cfg5(of, dev, peak, rank, world, args.chain_frames)
+        t5 = torch.tensor([ms5, ms5g if isinstance(ms5g, float) else -1.0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t5, op=dist.ReduceOp.MAX)
-        ms5 = float(t5.item())
+        ms5 = float(t5[0].item())
         px5 = args.chain_frames * 2160 * 3840
         e5 = _entry(ms5, px5, 155, peak * world)
+        if isinstance(ms5g, float) and float(t5[1].item()) > 0:
+            g5 = _entry(float(t5[1].item()), px5, 155, peak * world)
+            e5['cuda_graph_replay'] = {'ms': g5['ms'], 'Mpix/s': g5['Mpix/s'], 'frac_of_hbm': g5['frac_of_hbm'],
+                                       'what': 'the same chain (fwd + bwd) captured once with torch.cuda.graph and '
+                                               'replayed; all kernels run per replay, Python dispatch removed'}
+        elif ms5g is not None:
+            e5['cuda_graph_replay'] = ms5g
         e5.update({'frames_total': args.chain_frames, 'frames_per_rank': mine, 'n_gpus': world, 'scaling': 'strong',
                    'what': 'acc = acc.combine_with(f_i, 3); acc.apply(img, return_valid_area=True); one backward '
                            'through the chain; time = max over ranks; frac is of n_gpus x the HBM peak'})
@@ -510,6 +561,7 @@ def main():
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': workload, 'per_gpu_batch': n, 'global_batch': n * world,
+                       'validation': args.validation,
                        'parallelism': 'batch shards, one per GPU, no collective',
                        'l2': 'inputs (%.1f GB per step) exceed the 126 MB L2; no flush needed' % (
                            (BYTES_PER_PX['ofb_warp_t_fwd'] + BYTES_PER_PX['ofb_warp_t_bwd']) * px / 1e9)},

@@ -72,6 +72,12 @@ int ofb_selftest_div(float d, uint32_t lo_bits, uint32_t hi_bits, unsigned long 
 int ofb_flow_stats(const float *flow, const uint8_t *mask, int32_t *flags,
                    int N, int H, int W, void *stream);
 
+/* ofb_flow_stats with a batch summary: flags has N + 1 entries (zero on entry); flags[N] receives the OR over all
+ * items -- the word the device-side early-outs of ofb_warp_t_fwd_ex / ofb_warp_t_bwd_ex test, i.e. what the
+ * reference's all(is_zero_flow(..)) over the batch looks at (utils.py:497, flow_class.py:1046,1729,1738). */
+int ofb_flow_stats_batch(const float *flow, const uint8_t *mask, int32_t *flags,
+                         int N, int H, int W, void *stream);
+
 /* W -- backward warp of a payload by a target-referenced flow, with fused validity.
  * Replaces apply_flow(ref='t') (utils.py:541-555: grid - flow, normalise_coords, grid_sample(bilinear,
  * zeros, align_corners=True)) and, when `valid` is given, the mask tracking of Flow.apply
@@ -100,6 +106,42 @@ int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sign,
                    const float *gout, float add_flow,
                    float *gflow, float *gsrc, int64_t gsrc_bs,
                    int N, int C, int H, int W, void *stream);
+
+/* The reference's zero-flow early-outs decided ON THE DEVICE (no host synchronisation).
+ * ofb_early_decide evaluates up to three rules against the batch summary words of two flag arrays and leaves the
+ * decision in *sel (device int32): 0 = none, or the action of the first rule that fired.
+ *   flow_flags, payload_flags   int32[N + 1] as written by ofb_flow_stats_batch (or the out_flags of an earlier
+ *                               ofb_warp_t_fwd_ex) for the warping flow and for the payload when it is itself a flow;
+ *                               may be NULL
+ *   rules                       one rule per byte, tested in order; a rule fires when its OFB_STAT bit is CLEAR in
+ *                               flags[N]:   bit 7     rule present
+ *                                           bit 5     0: test flow_flags, 1: test payload_flags
+ *                                           bits 2-4  log2 of the OFB_STAT_* bit
+ *                                           bits 0-1  action
+ *   actions   1  out = add_flow*flow + src,  valid = src_mask & flow_mask   (apply_flow's early-out, utils.py:497-498)
+ *             2  out = src,                  valid = src_mask               (combine_with hands back one of its
+ *             3  out = add_flow*flow,        valid = flow_mask               inputs, flow_class.py:1729-1744)
+ * ofb_warp_t_fwd_ex / ofb_warp_t_bwd_ex are ofb_warp_t_fwd / ofb_warp_t_bwd honouring *sel (NULL = no early-out);
+ * the adjoint must be given the same sel.  out_flags (NULL ok; needs C == 2 and valid, i.e. a flow-valued result)
+ * receives the OFB_STAT_* flags of (out, valid): int32[ofb_warp_t_flags_ints(N, H, W)], the first N + 1 entries are
+ * the flags and must be zero on entry, the rest is workspace. */
+int ofb_early_decide(const int32_t *flow_flags, const int32_t *payload_flags, int rules, int N, int32_t *sel,
+                     void *stream);
+int64_t ofb_warp_t_flags_ints(int N, int H, int W);
+int ofb_warp_t_fwd_ex(const float *flow, int64_t flow_bs, float flow_sign,
+                      const float *src, int64_t src_bs,
+                      const uint8_t *src_mask, int64_t src_mask_bs,
+                      const uint8_t *flow_mask, int64_t flow_mask_bs,
+                      float add_flow, float valid_thresh,
+                      float *out, uint8_t *valid,
+                      int N, int C, int H, int W,
+                      const int32_t *sel, int32_t *out_flags, void *stream);
+int ofb_warp_t_bwd_ex(const float *flow, int64_t flow_bs, float flow_sign,
+                      const float *src, int64_t src_bs,
+                      const float *gout, float add_flow,
+                      float *gflow, float *gsrc, int64_t gsrc_bs,
+                      int N, int C, int H, int W,
+                      const int32_t *sel, void *stream);
 
 /* Windowed W: the flow/out/valid/flow_mask tensors cover an H x W WINDOW located at (window[0], window[1]) = (y0, x0)
  * of a global field of window[2] x window[3] pixels; coordinates, the round trip and zero padding live in the global

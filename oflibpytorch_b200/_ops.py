@@ -21,10 +21,12 @@ VALID_NONE, VALID_GT, VALID_EQ1 = 0, 1, 2
 
 _lib = torch.library.Library("oflib_b200", "DEF")
 _lib.define("flow_stats(Tensor flow, Tensor? mask) -> Tensor")
+_lib.define("flow_stats_batch(Tensor flow, Tensor? mask) -> Tensor")
 _lib.define("warp_t_fwd(Tensor flow, float sign, Tensor? src, Tensor? src_mask, Tensor? flow_mask, "
-            "float add_flow, float thresh, bool want_valid) -> (Tensor, Tensor)")
+            "float add_flow, float thresh, bool want_valid, Tensor? sel, bool want_flags) -> (Tensor, Tensor, Tensor)")
+_lib.define("early_decide(Tensor? fflags, Tensor? pflags, int rules, int n) -> Tensor")
 _lib.define("warp_t_bwd(Tensor flow, float sign, Tensor src, Tensor gout, float add_flow, "
-            "bool need_gflow, bool need_gsrc) -> (Tensor, Tensor)")
+            "bool need_gflow, bool need_gsrc, Tensor? sel) -> (Tensor, Tensor)")
 _lib.define("splat_s_fwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor? data, Tensor? data_mask, "
             "Tensor? flow_mask, bool occlude_zero, int valid_mode, bool want_aux, int[] window) -> "
             "(Tensor, Tensor, Tensor, Tensor, Tensor)")
@@ -113,7 +115,45 @@ def _flow_stats(flow: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tenso
     return flags
 
 
-def _warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid) -> Tuple[torch.Tensor, torch.Tensor]:
+def _flow_stats_batch(flow: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """(N + 1,) int32 on the device: per-item OFB_STAT_* bits and, last, their OR over the batch.  No sync."""
+    require_cuda(flow, "flow")
+    flow = _f32c(flow)
+    mask = _maskc(mask)
+    n, _, h, w = flow.shape
+    if mask is not None and mask.shape[0] != n:
+        mask = mask.expand(n, -1, -1).contiguous()
+    with torch.cuda.device(flow.device):
+        flags = torch.zeros((n + 1,), dtype=torch.int32, device=flow.device)
+        _call("ofb_flow_stats_batch", _p(flow), _p(mask), _p(flags), n, h, w, _stream())
+    return flags
+
+
+def early_rule(which: str, stat_bit: int, action: int) -> int:
+    """One rule byte of ofb_warp_t_fwd_ex: fires when `stat_bit` (an OFB_STAT_* value) is clear in the batch summary of
+    the warping flow's ('f') or the payload flow's ('p') flags.  action 1: identity (+ add_flow*flow), both masks;
+    2: the payload and its mask; 3: add_flow*flow and the flow mask."""
+    return 0x80 | (0x20 if which == 'p' else 0) | ((int(stat_bit).bit_length() - 1) << 2) | action
+
+
+def early_rules(*rules: int) -> int:
+    prog = 0
+    for k, r in enumerate(rules):
+        prog |= r << (8 * k)
+    return prog
+
+
+def _early_decide(fflags, pflags, rules, n) -> torch.Tensor:
+    """(1,) int32 on the device: which early-out (0 = none) the rules select for these flags.  No sync."""
+    t = fflags if fflags is not None else pflags
+    with torch.cuda.device(t.device):
+        sel = torch.empty((1,), dtype=torch.int32, device=t.device)
+        _call("ofb_early_decide", _p(fflags), _p(pflags), int(rules), int(n), _p(sel), _stream())
+    return sel
+
+
+def _warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid, sel=None,
+                want_flags=False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     require_cuda(flow, "flow")
     flow = _f32c(flow)
     src = None if src is None else _f32c(src)
@@ -126,16 +166,26 @@ def _warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_val
     with torch.cuda.device(dev):
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
         valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
-        _call("ofb_warp_t_fwd", 
-            _p(flow), _bs(flow, n, 2 * hw), sign,
-            _p(src) if c else None, _bs(src, n, c * hw),
-            _p(src_mask), _bs(src_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
-            add_flow, thresh, _p(out) if c else None, _p(valid) if want_valid else None,
-            n, c, h, w, _stream())
-    return out, valid
+        head = (_p(flow), _bs(flow, n, 2 * hw), sign,
+                _p(src) if c else None, _bs(src, n, c * hw),
+                _p(src_mask), _bs(src_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
+                add_flow, thresh, _p(out) if c else None, _p(valid) if want_valid else None,
+                n, c, h, w)
+        if sel is not None or want_flags:
+            if want_flags:      # flags (zeroed) followed by the kernel's workspace (ofb_warp_t_flags_ints)
+                buf = torch.empty((int(_native.lib().ofb_warp_t_flags_ints(n, h, w)),), dtype=torch.int32, device=dev)
+                out_flags = buf[:n + 1]
+                out_flags.zero_()
+            else:
+                buf = out_flags = torch.empty((0,), dtype=torch.int32, device=dev)
+            _call("ofb_warp_t_fwd_ex", *head, _p(sel), _p(buf) if want_flags else None, _stream())
+        else:
+            out_flags = torch.empty((0,), dtype=torch.int32, device=dev)
+            _call("ofb_warp_t_fwd", *head, _stream())
+    return out, valid, out_flags
 
 
-def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc) -> Tuple[torch.Tensor, torch.Tensor]:
+def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc, sel=None) -> Tuple[torch.Tensor, torch.Tensor]:
     require_cuda(flow, "flow")
     flow, src, gout = _f32c(flow), _f32c(src), _f32c(gout)
     n, c, h, w = gout.shape
@@ -144,10 +194,13 @@ def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc) -> Tuple
     with torch.cuda.device(dev):
         gflow = torch.empty((n, 2, h, w) if need_gflow else (0,), dtype=torch.float32, device=dev)
         gsrc = torch.empty(tuple(src.shape) if need_gsrc else (0,), dtype=torch.float32, device=dev)
-        _call("ofb_warp_t_bwd", 
-            _p(flow), _bs(flow, n, 2 * hw), sign, _p(src), _bs(src, n, c * hw), _p(gout), add_flow,
-            _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None, _bs(src, n, c * hw),
-            n, c, h, w, _stream())
+        head = (_p(flow), _bs(flow, n, 2 * hw), sign, _p(src), _bs(src, n, c * hw), _p(gout), add_flow,
+                _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None, _bs(src, n, c * hw),
+                n, c, h, w)
+        if sel is not None:
+            _call("ofb_warp_t_bwd_ex", *head, _p(sel), _stream())
+        else:
+            _call("ofb_warp_t_bwd", *head, _stream())
     return gflow, gsrc
 
 
@@ -234,6 +287,8 @@ def _splat_s_bwd(cx, cy, relative, sign, data, flow_mask, occlude_zero, out, den
 
 
 _lib.impl("flow_stats", _flow_stats, "CUDA")
+_lib.impl("flow_stats_batch", _flow_stats_batch, "CUDA")
+_lib.impl("early_decide", _early_decide, "CUDA")
 _lib.impl("warp_t_fwd", _warp_t_fwd, "CUDA")
 _lib.impl("warp_t_bwd", _warp_t_bwd, "CUDA")
 _lib.impl("splat_s_fwd", _splat_s_fwd, "CUDA")
@@ -255,27 +310,28 @@ def _reduce_to(g: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
 
 class _WarpT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, flow, src, src_mask, flow_mask, sign, add_flow, thresh, want_valid):
-        out, valid = _ops.warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid)
-        ctx.save_for_backward(flow, src)
+    def forward(ctx, flow, src, src_mask, flow_mask, sign, add_flow, thresh, want_valid, sel, want_flags):
+        out, valid, out_flags = _ops.warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid,
+                                                sel, want_flags)
+        ctx.save_for_backward(flow, src, sel)
         ctx.sign, ctx.add_flow = sign, add_flow
-        ctx.mark_non_differentiable(valid)
+        ctx.mark_non_differentiable(valid, out_flags)
         ctx.set_materialize_grads(False)     # no zero-filled stand-in for the gradient of the boolean output
-        return out, valid
+        return out, valid, out_flags
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gout, _gvalid):
-        flow, src = ctx.saved_tensors
+    def backward(ctx, gout, _gvalid, _gflags):
+        flow, src, sel = ctx.saved_tensors
         need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gflow = gsrc = None
         if gout is not None and (need_gflow or need_gsrc):
-            gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc)
+            gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc, sel)
             if need_gflow:
                 gflow = _reduce_to(gf, flow)
             if need_gsrc:
                 gsrc = gs
-        return gflow, gsrc, None, None, None, None, None, None
+        return gflow, gsrc, None, None, None, None, None, None, None, None
 
 
 class _SplatS(torch.autograd.Function):
@@ -312,13 +368,31 @@ def flow_stats(flow: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch
     return _ops.flow_stats(flow.detach(), mask)
 
 
+def flow_stats_batch(flow: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N + 1,) int32 on the device: per-item OFB_STAT_* bits, then their OR over the batch."""
+    return _ops.flow_stats_batch(flow.detach(), mask)
+
+
 def warp_t(flow, src, src_mask=None, flow_mask=None, sign=1.0, add_flow=0.0, thresh=0.99999,
-           want_valid=False):
-    """W.  Returns (out, valid); valid is an empty tensor unless want_valid.  src may be None (C = 0)."""
+           want_valid=False, fflags=None, pflags=None, early=0, want_flags=False):
+    """W.  Returns (out, valid), or (out, valid, out_flags) with `want_flags`; valid is an empty tensor unless
+    want_valid.  src may be None (C = 0).  fflags / pflags / early: device-side early-outs (ofb_early_decide)."""
+    sel = None
+    if early:
+        f = flow.detach()
+        n = _batch(f.shape[0], src, src_mask, flow_mask)
+        for fl in (fflags, pflags):
+            if fl is not None and fl.shape[0] != n + 1:
+                raise ValueError("oflibpytorch_b200: device flags of a batch of %d used with a batch of %d"
+                                 % (fl.shape[0] - 1, n))
+        sel = _ops.early_decide(fflags, pflags, int(early), n)
     if src is None:
-        return _ops.warp_t_fwd(flow.detach(), float(sign), None, src_mask, flow_mask, 0.0, float(thresh), True)
-    return _WarpT.apply(flow, src, src_mask, flow_mask, float(sign), float(add_flow), float(thresh),
-                        bool(want_valid))
+        out, valid, fl = _ops.warp_t_fwd(flow.detach(), float(sign), None, src_mask, flow_mask, 0.0, float(thresh), True,
+                                         sel, False)
+    else:
+        out, valid, fl = _WarpT.apply(flow, src, src_mask, flow_mask, float(sign), float(add_flow), float(thresh),
+                                      bool(want_valid), sel, bool(want_flags))
+    return (out, valid, fl) if want_flags else (out, valid)
 
 
 def splat_flow(flow, data, data_mask=None, flow_mask=None, sign=1.0, occlude_zero=True, valid_mode=VALID_NONE,

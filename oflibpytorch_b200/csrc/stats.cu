@@ -27,7 +27,7 @@ constexpr int kStatsIters = 8;
 template <int VEC>
 __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict__ flow,
                                                          const uint8_t *__restrict__ mask,
-                                                         int32_t *__restrict__ flags, int HW)
+                                                         int32_t *__restrict__ flags, int HW, int summary)
 {
     const int n = blockIdx.y;
     const float *f = flow + (int64_t)n * 2 * HW;
@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict
             if (masked != 0) fl |= OFB_STAT_NONZERO_M;
             if (masked >= thr) fl |= OFB_STAT_NONZERO_TM;
             if ((*reinterpret_cast<volatile int32_t *>(flags + n) & fl) != fl) atomicOr(flags + n, fl);
+            // batch summary (OR over the items): what the reference's all(is_zero_flow(..)) looks at (utils.py:497)
+            if (summary >= 0 && (*reinterpret_cast<volatile int32_t *>(flags + summary) & fl) != fl)
+                atomicOr(flags + summary, fl);
         }
     }
 }
@@ -105,8 +108,8 @@ extern "C" int ofb_selftest_div(float d, uint32_t lo_bits, uint32_t hi_bits, uns
     return 0;
 }
 
-extern "C" int ofb_flow_stats(const float *flow, const uint8_t *mask, int32_t *flags,
-                              int N, int H, int W, void *stream)
+static int flow_stats_impl(const float *flow, const uint8_t *mask, int32_t *flags, int N, int H, int W, int summary,
+                           void *stream)
 {
     if (!flow || !flags || N <= 0 || H <= 0 || W <= 0) return OFB_EINVAL;
     if ((int64_t)H * W > 0x3fffffff || N > 65535) return OFB_EINVAL;
@@ -117,8 +120,20 @@ extern "C" int ofb_flow_stats(const float *flow, const uint8_t *mask, int32_t *f
     int gx = (HW + per_block - 1) / per_block;
     if (gx < 1) gx = 1;
     const dim3 grid(gx, N);
-    if (vec4) flow_stats_kernel<4><<<grid, 256, 0, st>>>(flow, mask, flags, HW);
-    else flow_stats_kernel<1><<<grid, 256, 0, st>>>(flow, mask, flags, HW);
+    if (vec4) flow_stats_kernel<4><<<grid, 256, 0, st>>>(flow, mask, flags, HW, summary);
+    else flow_stats_kernel<1><<<grid, 256, 0, st>>>(flow, mask, flags, HW, summary);
     OFB_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int ofb_flow_stats(const float *flow, const uint8_t *mask, int32_t *flags,
+                              int N, int H, int W, void *stream)
+{
+    return flow_stats_impl(flow, mask, flags, N, H, W, -1, stream);
+}
+
+extern "C" int ofb_flow_stats_batch(const float *flow, const uint8_t *mask, int32_t *flags,
+                                    int N, int H, int W, void *stream)
+{
+    return flow_stats_impl(flow, mask, flags, N, H, W, N, stream);
 }

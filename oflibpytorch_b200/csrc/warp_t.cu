@@ -30,6 +30,9 @@ struct WarpFwdParams {
     float *out; uint8_t *valid;
     int N, C, H, W;
     Window win;
+    // device-side early-out decision (ofb_early_decide) and the flags of the result (combine mode 3 chains):
+    // out_flags = int32[N + 1] flags, followed by the per-CTA partial maxima the finishing kernel reduces
+    const int32_t *sel; int32_t *out_flags;
 };
 
 // Per-thread base pointers of one batch item (computed once; everything below is 32-bit offsets from them).
@@ -43,10 +46,14 @@ struct ItemPtrs {
 
 // One output pixel through global memory: channels [0, CN) (CN = 0: cn_rt channels, runtime loop).
 // pix = y*W + x of the output pixel; c_first = absolute index of channel 0 (for add_flow).
-template <int CN, bool WANT_VALID, bool ALL_IN>
+struct OutStats { unsigned all, masked; };   // largest |component| of the result as a bit pattern (stats.cu)
+
+template <int CN, bool WANT_VALID, bool ALL_IN, bool STATS = false>
 __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const Window &wn, const ItemPtrs &ip,
-                                                  const PixGeom &g, int pix, float fx, float fy, int c_first, int cn_rt)
+                                                  const PixGeom &g, int pix, float fx, float fy, int c_first, int cn_rt,
+                                                  OutStats *os = nullptr)
 {
+    unsigned okbit = 1u;
     const int HW = p.H * p.W;                       // output / flow plane
     const int HWs = wn.sh * wn.sw, W = wn.sw;       // stored source plane and its row pitch
     if (WANT_VALID) {
@@ -63,6 +70,7 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
         bool ok = blend4(g, a, b, c, d) > p.thresh;                                  // flow_class.py:898,922
         if (ip.fmask) ok = ok && (__ldg(ip.fmask + pix) != 0);                       // flow_class.py:934
         ip.valid[pix] = ok ? 1 : 0;
+        okbit = ok ? 1u : 0u;
     }
     if (CN > 0) {
 #pragma unroll
@@ -74,6 +82,11 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
             if (p.add_flow != 0.0f && c_first + c < 2)                               // flow_class.py:1804,1808
                 r = __fadd_rn(__fmul_rn(p.add_flow, (c_first + c) == 0 ? fx : fy), r);
             ip.out[c * HW + pix] = r;
+            if (STATS) {
+                const unsigned u = __float_as_uint(r) & 0x7fffffffu;
+                os->all = max(os->all, u);
+                os->masked = max(os->masked, u * okbit);
+            }
         }
     } else {
 #pragma unroll 1
@@ -91,16 +104,84 @@ __device__ __forceinline__ void warp_pixel_direct(const WarpFwdParams &p, const 
 
 // dispatch on the warp-uniform "every tap of every lane is inside the image" predicate (true for all but the
 // warps that sample near the image border)
-template <int CN, bool WANT_VALID>
+template <int CN, bool WANT_VALID, bool STATS = false>
 __device__ __forceinline__ void warp_pixel(const WarpFwdParams &p, const Window &wn, const ItemPtrs &ip, const PixGeom &g,
-                                           int pix, float fx, float fy, int c_first, int cn_rt)
+                                           int pix, float fx, float fy, int c_first, int cn_rt, OutStats *os = nullptr)
 {
-#ifdef OFB_ALLIN_FASTPATH
-    if (__all_sync(__activemask(), g.pnw && g.pne && g.psw && g.pse))
-        warp_pixel_direct<CN, WANT_VALID, true>(p, wn, ip, g, pix, fx, fy, c_first, cn_rt);
-    else
-#endif
-        warp_pixel_direct<CN, WANT_VALID, false>(p, wn, ip, g, pix, fx, fy, c_first, cn_rt);
+    warp_pixel_direct<CN, WANT_VALID, false, STATS>(p, wn, ip, g, pix, fx, fy, c_first, cn_rt, os);
+}
+
+// Device-side early-outs.  The reference decides on the host whether a flow is "all zero" and then returns one of its
+// inputs unchanged (utils.py:497-498, flow_class.py:1729-1744); deciding here, from the flags ofb_flow_stats_batch left
+// on the device, gives the same results without a host synchronisation.  `rules` holds up to three rules, one per byte,
+// evaluated in order: bit 7 set = rule present, bit 5 = which flags (0: warping flow, 1: payload flow), bits 2-4 =
+// log2 of the OFB_STAT_* bit that must be CLEAR in the batch summary word flags[N], bits 0-1 = what to do:
+//   1  out = add_flow * flow + src,  valid = src_mask & flow_mask      (apply with a zero flow; A zero in combine)
+//   2  out = src,                    valid = src_mask                  ("return the payload flow")
+//   3  out = add_flow * flow,        valid = flow_mask                 ("return the warping flow")
+// One thread evaluates the rules ONCE per call and leaves the decision in *sel; the warp kernels and their adjoints
+// read that single word (every CTA testing the flags itself cost 6-18 % of the kernel, measured).
+__global__ void early_decide_kernel(const int32_t *fflags, const int32_t *pflags, int rules, int N, int32_t *sel)
+{
+    int r = 0;
+    for (int k = 0; k < 3 && r == 0; ++k) {
+        const int rule = (rules >> (8 * k)) & 0xff;
+        if (!(rule & 0x80)) break;
+        const int32_t *fl = (rule & 0x20) ? pflags : fflags;
+        if (fl && !(fl[N] & (1 << ((rule >> 2) & 7)))) r = rule & 3;
+    }
+    *sel = r;
+}
+
+// per-lane variant for the cold early-out kernel (no warp collective: lanes may sit on different items)
+__device__ __forceinline__ void publish_stats_lane(int32_t *flags, int n, int N, unsigned all, unsigned masked)
+{
+    if (all == 0) return;
+    const unsigned thr = __float_as_uint(OFB_THRESHOLD);
+    int fl = OFB_STAT_NONZERO;
+    if (all >= 0x7f800000u) fl |= OFB_STAT_NONFINITE;
+    if (all >= thr) fl |= OFB_STAT_NONZERO_T;
+    if (masked != 0) fl |= OFB_STAT_NONZERO_M;
+    if (masked >= thr) fl |= OFB_STAT_NONZERO_TM;
+    if ((*reinterpret_cast<volatile int32_t *>(flags + n) & fl) != fl) atomicOr(flags + n, fl);
+    if ((*reinterpret_cast<volatile int32_t *>(flags + N) & fl) != fl) atomicOr(flags + N, fl);
+}
+
+// flags of a result: every CTA leaves its two maxima in the workspace behind the flags with plain stores (no atomics,
+// no same-address traffic, nothing to wait for); stats_finish_kernel folds them.  Reached by every thread of the CTA.
+__device__ __forceinline__ void publish_stats(int32_t *flags, int N, unsigned all, unsigned masked)
+{
+    __shared__ unsigned s_all[8], s_masked[8];
+    all = __reduce_max_sync(0xffffffffu, all);
+    masked = __reduce_max_sync(0xffffffffu, masked);
+    if ((threadIdx.x & 31) == 0) { s_all[threadIdx.x >> 5] = all; s_masked[threadIdx.x >> 5] = masked; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { all = max(all, s_all[k]); masked = max(masked, s_masked[k]); }
+        const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        unsigned *ws = reinterpret_cast<unsigned *>(flags + (N + 1));
+        ws[2 * cta] = all;
+        ws[2 * cta + 1] = masked;
+    }
+}
+
+// one CTA per batch item: fold the item's partial maxima into its flags and into the batch summary
+__global__ void __launch_bounds__(256) stats_finish_kernel(int32_t *flags, int N, int ctas_per_item)
+{
+    const int n = blockIdx.x;
+    const unsigned *ws = reinterpret_cast<const unsigned *>(flags + (N + 1)) + (int64_t)n * ctas_per_item * 2;
+    unsigned all = 0, masked = 0;
+    for (int i = threadIdx.x; i < ctas_per_item; i += 256) { all = max(all, ws[2 * i]); masked = max(masked, ws[2 * i + 1]); }
+    __shared__ unsigned s_all[8], s_masked[8];
+    all = __reduce_max_sync(0xffffffffu, all);
+    masked = __reduce_max_sync(0xffffffffu, masked);
+    if ((threadIdx.x & 31) == 0) { s_all[threadIdx.x >> 5] = all; s_masked[threadIdx.x >> 5] = masked; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { all = max(all, s_all[k]); masked = max(masked, s_masked[k]); }
+        publish_stats_lane(flags, n, N, all, masked);
+    }
 }
 
 __device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, const Window &wn, int n, int c_off)
@@ -126,20 +207,67 @@ __device__ __forceinline__ ItemPtrs item_ptrs(const WarpFwdParams &p, const Wind
 #endif
 constexpr int kDirRows = OFB_FWD_ROWS;    // rows per thread; CTA tile = 64 x 4*rows (2 warps across x, 4 across y)
 
-template <int CN, bool WANT_VALID, bool WIN>
+// The early-out results are plain copies.  They live in a kernel of their own (launched behind the warp whenever rules
+// are given; it returns at once unless a rule fired) so that the warp kernel keeps its 32 registers.
+__global__ void __launch_bounds__(256) warp_fwd_early_kernel(const WarpFwdParams p)
+{
+    const int sel = *p.sel;
+    if (!sel) return;
+    const int HW = p.H * p.W;
+    if (p.out_flags) {      // the warp's own partial maxima describe a result that is being replaced
+        const int64_t words = 2 * (int64_t)p.N * (((p.W + 63) / 64) * ((p.H + 4 * kDirRows - 1) / (4 * kDirRows)));
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+            p.out_flags[p.N + 1 + i] = 0;
+    }
+    unsigned all = 0, masked = 0;
+    int last_n = -1;
+    const int64_t total = (int64_t)p.N * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / HW), pix = (int)(i - (int64_t)n * HW);
+        if (n != last_n) {
+            if (p.out_flags && last_n >= 0) publish_stats_lane(p.out_flags, last_n, p.N, all, masked);
+            all = masked = 0;
+            last_n = n;
+        }
+        const float *fl = p.flow + (int64_t)n * p.flow_bs;
+        unsigned ok = 1u;
+        if (p.valid) {
+            if (sel != 3 && p.src_mask) ok &= (p.src_mask[(int64_t)n * p.src_mask_bs + pix] != 0);
+            if (sel != 2 && p.flow_mask) ok &= (p.flow_mask[(int64_t)n * p.flow_mask_bs + pix] != 0);
+            p.valid[(int64_t)n * HW + pix] = (uint8_t)ok;
+        }
+        for (int c = 0; c < p.C; ++c) {
+            float v = (sel == 3) ? 0.0f : p.src[(int64_t)n * p.src_bs + (int64_t)c * HW + pix];
+            // add_flow * f is exact for add_flow = 1 (the only value in use); f + 0.0 = f
+            if (sel != 2 && p.add_flow != 0.0f && c < 2) v = __fadd_rn(__fmul_rn(p.add_flow, fl[c * HW + pix]), v);
+            p.out[((int64_t)n * p.C + c) * HW + pix] = v;
+            if (c < 2) {
+                const unsigned u = __float_as_uint(v) & 0x7fffffffu;
+                all = max(all, u);
+                masked = max(masked, u * ok);
+            }
+        }
+    }
+    if (p.out_flags && last_n >= 0) publish_stats_lane(p.out_flags, last_n, p.N, all, masked);
+}
+
+template <int CN, bool WANT_VALID, bool WIN, bool STATS = false>
 __global__ void __launch_bounds__(256, OFB_FWD_MINB) warp_t_fwd_direct_kernel(const WarpFwdParams p, const CoordCtx cc)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
     const int y0 = blockIdx.y * (4 * kDirRows) + (warp >> 1) * kDirRows;
     const int n = blockIdx.z;
-    if (x >= p.W) return;
+    // (an early-out decision is NOT tested here: the warp runs regardless and warp_fwd_early_kernel, launched behind
+    // it, overwrites the result in the rare case a rule fired -- testing per CTA cost 5-18 % of this kernel, measured)
+    const bool inside = x < p.W;
+    if (!STATS && !inside) return;
     const int HW = p.H * p.W;
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
     float fx[kDirRows], fy[kDirRows];
 #pragma unroll
     for (int r = 0; r < kDirRows; ++r) {
-        const int q = min(y0 + r, p.H - 1) * p.W + x;
+        const int q = min(y0 + r, p.H - 1) * p.W + min(x, p.W - 1);
         fx[r] = __ldg(fl + q);
         fy[r] = __ldg(fl + (HW + q));
     }
@@ -147,15 +275,17 @@ __global__ void __launch_bounds__(256, OFB_FWD_MINB) warp_t_fwd_direct_kernel(co
     const Window wn = WIN ? p.win : Window{0, 0, p.H, p.W, 0, 0, p.H, p.W};
     const float xf = (float)(x + wn.x0);
     const ItemPtrs ip = item_ptrs(p, wn, n, 0);
-    const int rows = min(kDirRows, p.H - y0);
+    const int rows = (STATS && !inside) ? 0 : min(kDirRows, p.H - y0);
+    OutStats os{0u, 0u};
 #pragma unroll
     for (int r = 0; r < kDirRows; ++r) {
         if (r >= rows) break;
         float ix, iy;
         sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r + wn.y0), ix, iy);
         const PixGeom g = pix_geom<WIN>(ix, iy, wn);
-        warp_pixel<CN, WANT_VALID>(p, wn, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C);
+        warp_pixel<CN, WANT_VALID, STATS>(p, wn, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C, &os);
     }
+    if (STATS) publish_stats(p.out_flags, p.N, os.all, os.masked);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -374,6 +504,41 @@ static StagedKernel staged_kernel(int cn, int vmode)
 #endif
 constexpr int kBwdRows = OFB_BWD_ROWS;     // rows per thread; CTA tile = 64 x 4*rows (2 warps across x, 4 across y)
 
+// adjoints of the early-out results (warp_fwd_early_kernel): 1 out = add_flow*flow + src, 2 out = src, 3 out = add_flow*flow.
+// Launched behind the adjoint kernel; when a rule fired it OVERWRITES gflow and gsrc (a broadcast payload's gradient is
+// the sum over the batch).
+__global__ void __launch_bounds__(256) warp_bwd_early_kernel(const WarpBwdParams p)
+{
+    const int sel = *p.sel;
+    if (!sel) return;
+    const int HW = p.H * p.W;
+    const int64_t total = (int64_t)p.N * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / HW), pix = (int)(i - (int64_t)n * HW);
+        const float *go = p.gout + (int64_t)n * p.C * HW;
+        float rx = 0.0f, ry = 0.0f;
+        for (int c = 0; c < p.C; ++c) {
+            const float g = go[(int64_t)c * HW + pix];
+            if (p.gsrc && p.gsrc_bs != 0) p.gsrc[(int64_t)n * p.gsrc_bs + (int64_t)c * HW + pix] = (sel != 3) ? g : 0.0f;
+            if (sel != 2 && c == 0) rx = p.add_flow * g;
+            if (sel != 2 && c == 1) ry = p.add_flow * g;
+        }
+        if (p.gsrc && p.gsrc_bs == 0 && n == 0) {
+            for (int c = 0; c < p.C; ++c) {
+                float sum = 0.0f;
+                if (sel != 3)
+                    for (int m = 0; m < p.N; ++m) sum += p.gout[((int64_t)m * p.C + c) * HW + pix];
+                p.gsrc[(int64_t)c * HW + pix] = sum;
+            }
+        }
+        if (p.gflow) {
+            float *gf = p.gflow + (int64_t)n * 2 * HW;
+            gf[pix] = rx;
+            gf[HW + pix] = ry;
+        }
+    }
+}
+
 template <int CN, bool GFLOW, bool GSRC, bool WIN>
 __global__ void __launch_bounds__(256, OFB_BWD_MINB) warp_t_bwd_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
                                                          const int accumulate_gflow)
@@ -540,14 +705,16 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
                            const uint8_t *flow_mask, int64_t flow_mask_bs,
                            float add_flow, float valid_thresh,
                            float *out, uint8_t *valid,
-                           int N, int C, int H, int W, const Window &win, void *stream)
+                           int N, int C, int H, int W, const Window &win, void *stream,
+                           const int32_t *sel = nullptr, int32_t *out_flags = nullptr)
 {
     if (!flow || N <= 0 || C < 0 || (C > 0 && (!src || !out)) || (C == 0 && !valid)) return OFB_EINVAL;
+    if (out_flags && (C != 2 || !valid)) return OFB_EINVAL;       // flags of a result: flow-valued results only
     if (add_flow != 0.0f && C != 2) return OFB_EINVAL;
     if (win.gh < 2 || win.gw < 2) return OFB_ESHAPE;
     if (!window_ok(win, H, W) || N > 65535) return OFB_EINVAL;
     WarpFwdParams p{flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
-                    add_flow, valid_thresh, out, valid, N, C, H, W, win};
+                    add_flow, valid_thresh, out, valid, N, C, H, W, win, sel, out_flags};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const CoordCtx cc{{(float)(win.gw - 1), 1.0f / (float)(win.gw - 1)}, {(float)(win.gh - 1), 1.0f / (float)(win.gh - 1)},
                       flow_sign};
@@ -556,7 +723,7 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     // staging over-fetches (1+g)^2 for a flow gradient g, and its load->TMA->compute phases do not overlap inside a
     // CTA), so the staged kernel is opt-in (OFB_TMA=1) until it is software-pipelined across tiles.
     static const bool use_tma = getenv("OFB_TMA") != nullptr;
-    bool staged = use_tma && C > 0 && W >= kTileW && H >= kTileH && window_is_identity(win, H, W);
+    bool staged = use_tma && C > 0 && W >= kTileW && H >= kTileH && window_is_identity(win, H, W) && !sel && !out_flags;
     const int vmode = !valid ? 0 : (src_mask ? 2 : 1);
     alignas(64) CUtensorMap mask_map;
     alignas(64) CUtensorMap src_maps[2];          // [0]: groups of kMaxCN channels, [1]: the remainder group
@@ -609,9 +776,21 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
             default: k = OFB_PICK(0); break;
         }
 #undef OFB_PICK
+        if (out_flags) {
+            if (!win_id) return OFB_EINVAL;
+            k = warp_t_fwd_direct_kernel<2, true, false, true>;
+        }
         k<<<grid, 256, 0, st>>>(p, cc);
     }
     OFB_CHECK_LAUNCH();
+    if (sel) {
+        warp_fwd_early_kernel<<<148 * 8, 256, 0, st>>>(p);
+        OFB_CHECK_LAUNCH();
+    }
+    if (out_flags) {
+        stats_finish_kernel<<<N, 256, 0, st>>>(out_flags, N, ((W + 63) / 64) * ((H + 4 * kDirRows - 1) / (4 * kDirRows)));
+        OFB_CHECK_LAUNCH();
+    }
     return 0;
 }
 
@@ -619,7 +798,7 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
                            const float *src, int64_t src_bs,
                            const float *gout, float add_flow,
                            float *gflow, float *gsrc, int64_t gsrc_bs,
-                           int N, int C, int H, int W, const Window &win, void *stream)
+                           int N, int C, int H, int W, const Window &win, void *stream, const int32_t *sel = nullptr)
 {
     if (!flow || !gout || N <= 0 || C <= 0 || (gflow && !src)) return OFB_EINVAL;
     if (add_flow != 0.0f && C != 2) return OFB_EINVAL;
@@ -630,8 +809,9 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     const CoordCtx cc{{(float)(win.gw - 1), 1.0f / (float)(win.gw - 1)}, {(float)(win.gh - 1), 1.0f / (float)(win.gh - 1)},
                       flow_sign};
     if (gsrc && window_is_identity(win, H, W)) {     // ring adjoint (warp_t_adj.cu); 1 = outside its domain
-        const WarpBwdParams rp{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, win};
-        const int rs = warp_t_bwd_ring_launch(rp, cc, st);
+        const WarpBwdParams rp{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, win,
+                               nullptr};
+        const int rs = sel ? 1 : warp_t_bwd_ring_launch(rp, cc, st);
         if (rs != 1) return rs;
     }
     // Optional L2-resident accumulation (OFB_BWD_CHUNK_MB > 0): walk the batch in chunks whose gradient image fits the
@@ -659,7 +839,7 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
         }
         WarpBwdParams p{flow + (int64_t)n0 * flow_bs, flow_bs, flow_sign, src ? src + (int64_t)n0 * src_bs : nullptr, src_bs,
                         gout + (int64_t)n0 * C * out_plane, add_flow, gflow ? gflow + (int64_t)n0 * 2 * out_plane : nullptr,
-                        gsrc ? gsrc + (int64_t)n0 * gsrc_bs : nullptr, gsrc_bs, nn, C, H, W, win};
+                        gsrc ? gsrc + (int64_t)n0 * gsrc_bs : nullptr, gsrc_bs, nn, C, H, W, win, sel};
         const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), nn);
         for (int c0 = 0; c0 < C; c0 += kMaxCN) {       // channel groups of <= 4; gflow accumulates across groups
             const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
@@ -667,6 +847,12 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
                 p, cc, c0, c0 > 0 ? 1 : 0);
             OFB_CHECK_LAUNCH();
         }
+    }
+    if (sel) {
+        const WarpBwdParams p{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, win,
+                              sel};
+        warp_bwd_early_kernel<<<148 * 8, 256, 0, st>>>(p);
+        OFB_CHECK_LAUNCH();
     }
     return 0;
 }
@@ -693,6 +879,49 @@ extern "C" int ofb_warp_t_bwd(const float *flow, int64_t flow_bs, float flow_sig
     if (H < 2 || W < 2) return OFB_ESHAPE;
     return warp_t_bwd_impl(flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W,
                            Window{0, 0, H, W, 0, 0, H, W}, stream);
+}
+
+// device-side early-out decision and the _ex variants that honour it (see include/oflib_b200.h)
+extern "C" int ofb_early_decide(const int32_t *flow_flags, const int32_t *payload_flags, int rules, int N, int32_t *sel,
+                                void *stream)
+{
+    if (!sel || N <= 0) return OFB_EINVAL;
+    early_decide_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(flow_flags, payload_flags, rules, N, sel);
+    OFB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int64_t ofb_warp_t_flags_ints(int N, int H, int W)
+{
+    const int64_t ctas = (int64_t)((W + 63) / 64) * ((H + 4 * kDirRows - 1) / (4 * kDirRows));
+    return (int64_t)N + 1 + 2 * ctas * N;
+}
+
+extern "C" int ofb_warp_t_fwd_ex(const float *flow, int64_t flow_bs, float flow_sign,
+                                 const float *src, int64_t src_bs,
+                                 const uint8_t *src_mask, int64_t src_mask_bs,
+                                 const uint8_t *flow_mask, int64_t flow_mask_bs,
+                                 float add_flow, float valid_thresh,
+                                 float *out, uint8_t *valid,
+                                 int N, int C, int H, int W,
+                                 const int32_t *sel, int32_t *out_flags, void *stream)
+{
+    if (H < 2 || W < 2) return OFB_ESHAPE;
+    return warp_t_fwd_impl(flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
+                           add_flow, valid_thresh, out, valid, N, C, H, W, Window{0, 0, H, W, 0, 0, H, W}, stream,
+                           sel, out_flags);
+}
+
+extern "C" int ofb_warp_t_bwd_ex(const float *flow, int64_t flow_bs, float flow_sign,
+                                 const float *src, int64_t src_bs,
+                                 const float *gout, float add_flow,
+                                 float *gflow, float *gsrc, int64_t gsrc_bs,
+                                 int N, int C, int H, int W,
+                                 const int32_t *sel, void *stream)
+{
+    if (H < 2 || W < 2) return OFB_ESHAPE;
+    return warp_t_bwd_impl(flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W,
+                           Window{0, 0, H, W, 0, 0, H, W}, stream, sel);
 }
 
 // Windowed variants: window[8] = {y0, x0, global_h, global_w, src_y0, src_x0, src_h, src_w} (see struct Window).

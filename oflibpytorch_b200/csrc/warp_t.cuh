@@ -98,6 +98,7 @@ struct WarpBwdParams {
     float *gflow; float *gsrc; int64_t gsrc_bs;
     int N, C, H, W;
     Window win;
+    const int32_t *sel;   // device-side early-out decision (ofb_early_decide), or nullptr
 };
 
 // Predicated fire-and-forget reduction: `@p red.global.add.f32 [a + imm], v` -- no branch, no return value.

@@ -24,7 +24,9 @@ import torch.nn.functional as f
 
 from . import _ops
 from ._ops import VALID_EQ1, VALID_GT, VALID_NONE
-from .utils import (STAT_NONFINITE, _is_zero_from_stats, _restore_dtype, _valid_vecs, get_pure_pytorch,
+from . import utils as _utils
+from .utils import (STAT_NONFINITE, STAT_NONZERO, STAT_NONZERO_M, STAT_NONZERO_T, STAT_NONZERO_TM,
+                    _is_zero_from_stats, _restore_dtype, _valid_vecs, get_pure_pytorch,
                     get_valid_device, get_valid_mask, get_valid_padding, get_valid_ref, get_valid_shape, track_pts)
 
 FlowAlias = 'Flow'
@@ -46,6 +48,8 @@ class Flow(object):
         :param device: tensor device; defaults to the device of `flow_vectors`
         """
         self._stats = None
+        self._dflags = None          # device copy of the flags (+ batch summary), see _get_dflags
+        self._user = True            # built from caller data: owes a finite test (deferred mode)
         # If the mask is already a device-resident bool tensor of the right shape, the single validation pass
         # over the vectors (finite test, utils.py:98) also yields the mask-aware zero flags (flow_class.py:1243).
         self._mask_hint = None
@@ -66,6 +70,7 @@ class Flow(object):
         """Internal: wrap kernel outputs (already N-2-H-W fp32 / N-H-W bool on one device)."""
         obj = cls.__new__(cls)
         obj._vecs, obj._ref, obj._mask, obj._device, obj._stats = vecs, ref, mask, vecs.device, None
+        obj._dflags, obj._user = None, False
         return obj
 
     # ------------------------------------------------------------------ properties
@@ -76,8 +81,10 @@ class Flow(object):
     @vecs.setter
     def vecs(self, input_vecs):
         hint = getattr(self, '_mask_hint', None)
-        v, stats = _valid_vecs(input_vecs, error_string="Error setting flow vectors: ", want_stats=True, mask=hint)
+        v, stats = _valid_vecs(input_vecs, error_string="Error setting flow vectors: ", want_stats=True, mask=hint,
+                               lazy_ok=True)
         self._vecs = v
+        self._dflags, self._user = None, True
         # without a mask hint the flags of this pass are unmasked; the masked bits are only trusted once a
         # mask-aware pass ran
         self._stats = None
@@ -109,12 +116,14 @@ class Flow(object):
                 self._stats = [fl | ((fl & 2) << 2) | ((fl & 4) << 2) for fl in self._stats_unmasked]
             else:
                 self._stats = None      # flags cached against the previous mask are stale: recomputed lazily
+            self._dflags = None
         else:
             m = get_valid_mask(input_mask, desired_shape=self.shape, error_string="Error setting flow mask: ")
             self._mask = m.to(self._vecs.device)
             hinted = getattr(self, '_stats_hinted', None)
             self._stats = hinted if (hinted is not None and input_mask is getattr(self, '_mask_hint', None)) else None
             self._stats_hinted = None
+            self._dflags = None
 
     @property
     def mask_numpy(self) -> np.ndarray:
@@ -324,12 +333,28 @@ class Flow(object):
         padding = [[int(v) for v in row] for row in torch.ceil(pads).tolist()]
         return padding[0] if item is not None else padding
 
-    def _get_stats(self) -> List[int]:
-        """Per-item OFB_STAT_* flags of (vecs, mask): one kernel, one sync, cached."""
-        if self._stats is None:
+    def _get_dflags(self) -> torch.Tensor:
+        """(N + 1,) int32 ON THE DEVICE: per-item OFB_STAT_* flags of (vecs, mask) and their OR over the batch.  One
+        kernel, no host sync; cached.  Results of the fused combine kernel arrive with their flags already set."""
+        if self._dflags is None:
             _ops.require_cuda(self._vecs, "flow")
-            self._stats = _ops.flow_stats(self._vecs, self._mask).tolist()
+            self._dflags = _ops.flow_stats_batch(self._vecs, self._mask)
+            if self._user and self._stats is None:       # not validated eagerly: the finite test is owed
+                _utils._defer_finite_check(self._dflags, "Error setting flow vectors: ")
+        return self._dflags
+
+    def _get_stats(self) -> List[int]:
+        """Per-item OFB_STAT_* flags of (vecs, mask) on the HOST: one kernel, one sync, cached."""
+        if self._stats is None:
+            flags = self._get_dflags().tolist()
+            if self._user and any(f & STAT_NONFINITE for f in flags):
+                raise ValueError("Error setting flow vectors: Input contains NaN, Inf or -Inf values")
+            self._stats = flags[:-1]
         return self._stats
+
+    @staticmethod
+    def _deferred() -> bool:
+        return _utils.get_validation() == 'deferred'
 
     def is_zero(self, thresholded: bool = None, masked: bool = None) -> torch.Tensor:
         """reference flow_class.py:1226-1244 (+ utils.py:919-938)"""
@@ -353,6 +378,13 @@ class Flow(object):
         Flow.apply, as one launch sequence.  For 't' the valid bit is ANDed with self.mask when `flow_mask_and`;
         for 's' `payload_mask` must already contain the AND with self.mask (flow_class.py:880-895).
         Includes the zero-flow early-out of apply_flow (utils.py:497-498)."""
+        if self._ref == 't' and self._deferred():
+            # the early-out (utils.py:497-498) is taken by the kernel from the device flags: no host sync
+            out, valid = _ops.warp_t(self._vecs, payload, payload_mask,
+                                     self._mask if (need_valid and flow_mask_and) else None,
+                                     sign=sign, thresh=0.99999, want_valid=need_valid, fflags=self._get_dflags(),
+                                     early=_ops.early_rules(_ops.early_rule('f', STAT_NONZERO_T, 1)))
+            return out, (valid if need_valid else None)
         if self._all_zero(thresholded=True, masked=False):
             n = max(payload.shape[0], self.shape[0], 1 if payload_mask is None else payload_mask.shape[0])
             out = payload
@@ -612,8 +644,13 @@ class Flow(object):
 
     # ------------------------------------------------------------------ valid areas (flow_class.py:1088-1172)
     def _valid_area(self, sign: float, splat: bool, consider_mask: bool) -> torch.Tensor:
+        if not splat and self._deferred():
+            _o, valid = _ops.warp_t(self._vecs, None, None, self._mask, sign=sign, thresh=0.9999, want_valid=True,
+                                    fflags=self._get_dflags(),
+                                    early=_ops.early_rules(_ops.early_rule('f', STAT_NONZERO_T, 1)))
+            return valid
         if self._all_zero(thresholded=True, masked=False):           # apply_flow's early-out returns its input
-            return self._mask.clone() if splat else self._mask.clone()
+            return self._mask.clone()
         if splat:
             _o, _d, _w, valid = _ops.splat_flow(self._vecs, None, None if consider_mask else self._mask,
                                                 self._mask if consider_mask else None,
@@ -652,6 +689,17 @@ class Flow(object):
         if not isinstance(thresholded, bool):
             raise TypeError("Error combining flows: Thresholded needs to be a boolean")
 
+        if mode == 3 and self._deferred():
+            # flow_class.py:1729-1744 and utils.py:497-498 as rules for the kernel (first match wins, like the
+            # reference's if-ladder): self zero -> `flow`; flow zero -> `self`; warping flow zero -> plain sum
+            bit = STAT_NONZERO_TM if thresholded else STAT_NONZERO_M
+            if self._ref == 's':        # v1 + W(-v1, [v2|m2]): self warps (f), flow is the payload (p)
+                rules = _ops.early_rules(_ops.early_rule('f', bit, 2), _ops.early_rule('p', bit, 3),
+                                         _ops.early_rule('f', STAT_NONZERO_T, 1))
+                return self._fused_warp_add(flow, sign=-1.0, rules=rules)
+            rules = _ops.early_rules(_ops.early_rule('p', bit, 3), _ops.early_rule('f', bit, 2),
+                                     _ops.early_rule('f', STAT_NONZERO_T, 1))
+            return flow._fused_warp_add(self, sign=1.0, rules=rules)
         if self._all_zero(thresholded, masked=True):                 # flow_class.py:1729-1744
             return flow
         if flow._all_zero(thresholded, masked=True):
@@ -721,9 +769,18 @@ class Flow(object):
         result._ref = ref
         return result
 
-    def _fused_warp_add(self, payload: FlowAlias, sign: float) -> FlowAlias:
+    def _fused_warp_add(self, payload: FlowAlias, sign: float, rules: int = 0) -> FlowAlias:
         """v_self + W(sign*v_self, [v_payload | m_payload]) with mask (theta(mask channel) & m_self).
-        Restates  self + Flow(sign*v_self,'t',m_self).apply(payload)  including apply_flow's early-out."""
+        Restates  self + Flow(sign*v_self,'t',m_self).apply(payload)  including apply_flow's early-out.
+        With `rules` (deferred validation) every early-out is decided by the kernel and the result carries its own
+        device flags, so a chain of combines never touches the host."""
+        if rules:
+            out, valid, fl = _ops.warp_t(self._vecs, payload._vecs, payload._mask, self._mask, sign=sign, add_flow=1.0,
+                                         thresh=0.99999, want_valid=True, fflags=self._get_dflags(),
+                                         pflags=payload._get_dflags(), early=rules, want_flags=True)
+            res = Flow._make(out, self._ref, valid)
+            res._dflags = fl
+            return res
         if self._all_zero(thresholded=True, masked=False):
             return Flow._make(self._vecs + payload._vecs, self._ref, payload._mask & self._mask)
         out, valid = _ops.warp_t(self._vecs, payload._vecs, payload._mask, self._mask, sign=sign, add_flow=1.0,

@@ -55,11 +55,72 @@ def unset_pure_pytorch(warn: bool = None):
 
 
 # ----------------------------------------------------------------------------------------------------
+# validation mode.  'eager' (default) is the reference's contract: a flow with NaN/Inf raises ValueError where it
+# is handed over (utils.py:98), which costs one device->host read per user-supplied flow.  'deferred' never
+# synchronises on the 't' path: the finite test and the zero-flow questions stay on the DEVICE (ofb_flow_stats_batch),
+# the reference's early-outs (utils.py:497-498, flow_class.py:1729-1744) are taken by the kernels themselves
+# (ofb_warp_t_fwd_ex), and a non-finite flow raises at the next `check_deferred()` instead of at construction.
+# ----------------------------------------------------------------------------------------------------
+_VALIDATION = 'eager'
+_PENDING = []          # [(device flags, message)] of flows whose finite test has not been read back yet
+
+
+def get_validation() -> str:
+    return _VALIDATION
+
+
+def set_validation(mode: str):
+    """'eager': reference behaviour (ValueError at hand-over, one host sync per user-supplied flow);
+    'deferred': no host sync on the 't' path, ValueError raised by `check_deferred()`."""
+    global _VALIDATION
+    if mode not in ('eager', 'deferred'):
+        raise ValueError("validation mode must be 'eager' or 'deferred', got {!r}".format(mode))
+    _VALIDATION = mode
+
+
+class validation(object):
+    """Context manager: ``with of.validation('deferred'): ...``"""
+
+    def __init__(self, mode: str):
+        self.mode, self.prev = mode, None
+
+    def __enter__(self):
+        self.prev = get_validation()
+        set_validation(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_validation(self.prev)
+        return False
+
+
+def _defer_finite_check(flags: torch.Tensor, error_string: str):
+    if len(_PENDING) >= 4096:          # bounded: drop the oldest entries unchecked rather than grow without limit
+        del _PENDING[:2048]
+    _PENDING.append((flags, error_string))
+
+
+def check_deferred():
+    """Read back the finite tests deferred since the last call (ONE host sync) and raise the reference's ValueError
+    (utils.py:98-99) if any flow handed over in 'deferred' mode held NaN, Inf or -Inf."""
+    pending, bad = list(_PENDING), None
+    del _PENDING[:]
+    if pending:
+        summary = torch.stack([f[-1] for f, _ in pending]).tolist()
+        for (_, msg), fl in zip(pending, summary):
+            if fl & STAT_NONFINITE:
+                bad = msg
+                break
+    if bad is not None:
+        raise ValueError(bad + "Input contains NaN, Inf or -Inf values")
+
+
+# ----------------------------------------------------------------------------------------------------
 # validation (reference utils.py:72-232) -- the error contract of the boundary
 # ----------------------------------------------------------------------------------------------------
 
 def _valid_vecs(vecs: Any, desired_shape=None, error_string: str = None, want_stats: bool = False,
-                mask: torch.Tensor = None):
+                mask: torch.Tensor = None, lazy_ok: bool = False):
     """get_valid_vecs plus, optionally, the host copy of the per-item OFB_STAT_* flags obtained in the same
     pass that checks for NaN/Inf (so that later zero-flow questions cost nothing)."""
     error_string = '' if error_string is None else error_string
@@ -80,10 +141,12 @@ def _valid_vecs(vecs: Any, desired_shape=None, error_string: str = None, want_st
     stats = None
     if vecs.is_cuda:
         v32 = vecs.float().contiguous()
-        flags = _ops.flow_stats(v32, mask).tolist()          # the one sync of the call
-        if any(f & STAT_NONFINITE for f in flags):
-            raise ValueError(error_string + "Input contains NaN, Inf or -Inf values")
-        stats = flags
+        if _VALIDATION == 'eager' or (want_stats and not lazy_ok):
+            flags = _ops.flow_stats(v32, mask).tolist()          # the one sync of the call
+            if any(f & STAT_NONFINITE for f in flags):
+                raise ValueError(error_string + "Input contains NaN, Inf or -Inf values")
+            stats = flags
+        # 'deferred': nothing is launched here; the caller computes device flags when (and if) it needs them
         vecs = v32
     else:
         if not torch.isfinite(vecs).all():
@@ -293,7 +356,9 @@ def apply_flow(flow: Union[np.ndarray, torch.Tensor], target: torch.Tensor, ref:
     :param mask: (H,W) or (N,H,W) flow mask, only relevant for 's' flows
     """
     ref = get_valid_ref(ref)
-    flow, stats = _valid_vecs(flow, error_string="Error applying flow to a target: ", want_stats=True)
+    # 'deferred' validation, 't' flows: finite test and zero-flow early-out stay on the device (no host sync)
+    flow, stats = _valid_vecs(flow, error_string="Error applying flow to a target: ", want_stats=True,
+                              lazy_ok=(ref == 't'))
     if stats is not None and all(_is_zero_from_stats(stats, True, False)):       # utils.py:497-498
         return target
     if not isinstance(target, torch.Tensor):
@@ -321,7 +386,12 @@ def apply_flow(flow: Union[np.ndarray, torch.Tensor], target: torch.Tensor, ref:
         raise ValueError("Error applying flow to target: Batch dimensions for flow ({}) and target ({}) don't match"
                          .format(flow.shape[0], t.shape[0]))
 
-    if ref == 't':
+    if ref == 't' and stats is None:
+        # the kernel takes the early-out itself (the result then equals `target`, broadcast to the flow's batch)
+        fl = _ops.flow_stats_batch(flow, None)
+        _defer_finite_check(fl, "Error applying flow to a target: ")
+        result, _ = _ops.warp_t(flow, t, fflags=fl, early=_ops.early_rules(_ops.early_rule('f', STAT_NONZERO_T, 1)))
+    elif ref == 't':
         result, _ = _ops.warp_t(flow, t)                                          # utils.py:541-555
     else:
         result, _d, _w, _v = _ops.splat_flow(flow, t, None, mask, 1.0, True, VALID_NONE)   # utils.py:576
