@@ -54,6 +54,18 @@ def measured_peak():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def python_reference_timing():
+    """The UNMODIFIED Python reference timed on the build container's CPU (baseline/time_reference_cpu.py): context
+    for the C/OpenMP port that `cpu_baseline` times on the GPU box (the reference itself cannot travel there)."""
+    try:
+        with open(os.path.join(ROOT, 'baseline', 'reference_cpu_timing.json')) as fh:
+            d = json.load(fh)
+        return {'what': d['reference'], 'cores': d['cores'], 'where': d['where'],
+                'Mpix/s': {k: v['Mpix/s'] for k, v in d['results'].items()}}
+    except Exception:
+        return None
+
+
 def known_traffic(name):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
     p = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -460,6 +472,8 @@ def main():
         # pinned host copies of the whole batch (9 GB per rank at the named config); if any rank cannot pin that much
         # (8 ranks on one host), every rank falls back to a quarter of the batch -- agreed collectively so that the
         # barriers below stay matched
+        from oflibpytorch_b200 import numa
+        numa_info = numa.bind_to_gpu_node(local_rank)     # pin from the GPU's own NUMA node (no-op on one node)
         e2e_n, host_in, host_out = n, None, None
         for attempt_n in (n, max(1, n // 4)):
             ok = 1
@@ -509,7 +523,8 @@ def main():
                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_step': float(t2.item()),
                'steps': k2, 'batch_per_gpu': e2e_n,
                'how': 'oflibpytorch_b200.streaming.HostWarpPipeline, chunk %d, pinned host buffers, '
-                      'H2D/compute/D2H on three streams' % args.e2e_chunk}
+                      'H2D/compute/D2H on three streams' % args.e2e_chunk,
+               'numa': numa_info}
         del host_in, host_out
 
     # ---------------------------------------------------------------- the rest of BASELINE.json's metric and configs
@@ -553,7 +568,9 @@ def main():
         r = cpu_reference_arm(3, 1, args.cpu_sample)
         cpu = {'value': r['value'], 'unit': 'Mpix/s', 'cores': r['cores'], 'kind': 'port',
                'sample': 'oracle (C/OpenMP restatement of the reference CPU path), batch %d x 1080p, fwd+bwd, '
-                         'mean of 3 steps' % r['sample_n']}
+                         'mean of 3 steps; the metric is per flow pixel and flat in the batch size, so the sample '
+                         'runs batch %d where the GPU arm runs %d' % (r['sample_n'], r['sample_n'], n),
+               'python_reference': python_reference_timing()}
 
     if rank == 0:
         line = {
