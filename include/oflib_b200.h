@@ -311,6 +311,13 @@ int ofb_resize_fwd(const float *flow, const uint8_t *mask, double scale_y, doubl
 int ofb_resize_bwd(const float *gout, double scale_y, double scale_x, float *gin,
                    int N, int H, int W, void *stream);
 
+/* Row-band sharding, halo step: dst[n, k] += src[n, k] for k < floats_per_item, n < N, with item
+ * strides in floats.  `src` is typically PEER memory (another GPU's halo rows, mapped through CUDA IPC / torch
+ * symmetric memory), read over NVLink by this kernel; called once per neighbour on one stream, which fixes the order
+ * of the additions (own + upper + lower). */
+int ofb_add_rows(float *dst, int64_t dst_item_stride, const float *src, int64_t src_item_stride,
+                 int N, int64_t floats_per_item, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

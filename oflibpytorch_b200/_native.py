@@ -52,6 +52,7 @@ SIGNATURES = {
     'ofb_splat_s_band_bwd_prepass': ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     'ofb_splat_s_band_bwd_gather': ([_P, _P, _L, _F, _P, _L, _P, _L, _I, _P, _P, _P, _P, _P, _L, _P,
                                      _I, _I, _I, _I, _P, _P], _I),
+    'ofb_add_rows': ([_P, _L, _P, _L, _I, _L, _P], _I),
     'ofb_sample_pts_fwd': ([_P, _L, _P, _P, _I, _I, _I, _I, _P], _I),
     'ofb_sample_pts_bwd': ([_P, _L, _P, _P, _P, _L, _P, _I, _I, _I, _I, _P], _I),
     'ofb_flow_extent': ([_P, _P, _I, _P, _I, _I, _I, _P], _I),

@@ -585,9 +585,27 @@ def sample_pts(flow, pts):
     return _SamplePts.apply(flow, pts)
 
 
-def splat_band_accumulate(flow, data, data_mask, flow_mask, sign, occlude_zero, band):
+def add_rows(dst: torch.Tensor, src: torch.Tensor):
+    """dst[l] += src[l] for every leading index l, where dst[l] / src[l] are contiguous runs of floats (views whose
+    leading dimension may be strided).  `src` may be PEER memory: the kernel reads it over NVLink (ofb_add_rows)."""
+    if dst.dtype != torch.float32 or src.dtype != torch.float32 or dst.shape != src.shape:
+        raise ValueError("oflibpytorch_b200: add_rows needs two fp32 tensors of equal shape")
+    if dst.numel() == 0:
+        return dst
+    n = dst.shape[0]
+    per = dst[0].numel()
+    if not (dst[0].is_contiguous() and src[0].is_contiguous()):
+        raise ValueError("oflibpytorch_b200: add_rows needs contiguous items")
+    with torch.cuda.device(dst.device):
+        _call("ofb_add_rows", _p(dst), dst.stride(0) if n > 1 else per, _p(src), src.stride(0) if n > 1 else per,
+              n, per, _stream())
+    return dst
+
+
+def splat_band_accumulate(flow, data, data_mask, flow_mask, sign, occlude_zero, band, out=None):
     """Row-band splat, step 1 (forward only): returns the interleaved accumulator (N, acc_h, W, KP) of this band.
-    band = (src_y0, global_h, acc_y0, acc_h); see include/oflib_b200.h ofb_splat_s_band_accumulate."""
+    band = (src_y0, global_h, acc_y0, acc_h); see include/oflib_b200.h ofb_splat_s_band_accumulate.  `out`: where to
+    accumulate (e.g. peer-mapped memory, so that the neighbours can read the halo rows in place)."""
     require_cuda(flow, "flow")
     flow = _f32c(flow.detach())
     data = None if data is None else _f32c(data.detach())
@@ -600,7 +618,12 @@ def splat_band_accumulate(flow, data, data_mask, flow_mask, sign, occlude_zero, 
         raise ValueError("oflibpytorch_b200: payloads wider than 6 channels are not supported by the row-band splat")
     hw = h * w
     with torch.cuda.device(flow.device):
-        acc = torch.empty((n, int(band[3]), w, kp), dtype=torch.float32, device=flow.device)
+        if out is not None:
+            acc = out
+            if tuple(acc.shape) != (n, int(band[3]), w, kp) or not acc.is_contiguous() or acc.dtype != torch.float32:
+                raise ValueError("oflibpytorch_b200: accumulator must be a contiguous fp32 (N, acc_h, W, KP) tensor")
+        else:
+            acc = torch.empty((n, int(band[3]), w, kp), dtype=torch.float32, device=flow.device)
         cx, cy = flow[:, 0], flow[:, 1]
         _call("ofb_splat_s_band_accumulate", _p(cx), _p(cy), 0 if (flow.shape[0] == 1 and n > 1) else 2 * hw, 1, sign,
               _p(data) if c else None, _bs(data, n, c * hw), _p(data_mask), _bs(data_mask, n, hw),
