@@ -56,6 +56,8 @@ void ofb_launch_count_reset(void);
 /* Tuning knobs for profiling sweeps (the defaults are the measured best; not needed in production).
  *   key 1  W adjoint implementation: -1 auto, 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA reduce flush
  *   key 2  W adjoint ring: output rows per warp task
+ *   key 4  S forward: 1 = deterministic merge (64-bit fixed-point accumulation: float outputs bit-identical from run
+ *          to run, about 3x slower), 0 = float atomics (default).  ofb_splat_s_workspace follows the mode.
  * Returns 0, or OFB_EINVAL for an unknown key.  Process-wide, not thread-safe. */
 int ofb_set_option(int key, int value);
 

@@ -13,7 +13,7 @@ from .utils import (DEFAULT_THRESHOLD, apply_flow, apply_s_flow, get_flow_endpoi
                     grid_from_unstructured_data, is_zero_flow, load_kitti, load_kitti_batch, load_sintel,
                     load_sintel_batch, load_sintel_mask, resize_flow, set_pure_pytorch, threshold_vectors,
                     track_pts, unset_pure_pytorch, check_deferred, get_validation, set_validation,
-                    validation)
+                    validation, set_deterministic)
 
 __version__ = '0.1.0'
 __all__ = ['Flow', 'combine_flows', 'invert_flow', 'switch_flow_ref', 'valid_source', 'valid_target',
@@ -21,4 +21,4 @@ __all__ = ['Flow', 'combine_flows', 'invert_flow', 'switch_flow_ref', 'valid_sou
            'threshold_vectors', 'track_pts', 'get_pure_pytorch', 'set_pure_pytorch', 'unset_pure_pytorch',
            'DEFAULT_THRESHOLD', 'get_flow_padding', 'resize_flow', 'load_sintel', 'load_sintel_batch',
            'load_sintel_mask', 'load_kitti', 'load_kitti_batch', 'set_validation', 'get_validation', 'validation',
-           'check_deferred']
+           'check_deferred', 'set_deterministic']

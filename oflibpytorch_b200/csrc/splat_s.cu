@@ -163,6 +163,125 @@ __global__ void __launch_bounds__(256) splat_normalise_kernel(const SplatParams 
 }
 
 // ------------------------------------------------------------------------------------------------
+// deterministic forward (opt-in, ofb_set_option key 4): the merge is done in 64-bit FIXED POINT.  Integer addition is
+// associative, so the accumulated sums -- and with them every float output -- are bit-identical from run to run
+// whatever order the L2 applies the atomics in ("deterministic global merge", reference order utils.py:1132-1144).
+//   numerators    round(w * d * 2^k),  2^k = 2^40 / 2^ceil(log2 max|d|)  (max|d| from one reduction pass; the product
+//                 w * d is exact in double, the power of two too: the only rounding is the final conversion)
+//   density, bad  max(1, round(w * 2^40)): a positive weight never quantises to zero, so `density > 0` (utils.py:1197)
+//                 and `bad == 0` keep their exact meaning
+// C + 2 planes of int64 per item, scalar 64-bit atomics: about 3x slower than the float path, which is why it is a
+// mode and not the default.
+// ------------------------------------------------------------------------------------------------
+int g_splat_det = 0;
+
+__global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ v, int64_t count, unsigned *out)
+{
+    unsigned m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(__ldg(v + i)) & 0x7fffffffu);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m != 0 && *reinterpret_cast<volatile unsigned *>(out) < m) atomicMax(out, m);
+}
+
+// 2^k with 2^k * max|d| in [2^39, 2^40]; 1 when the data are all zero or not finite
+__device__ __forceinline__ double det_scale(const unsigned *maxbits)
+{
+    const unsigned b = __ldg(maxbits);
+    if (b == 0 || b >= 0x7f800000u) return 1.0;
+    int e;
+    frexpf(__uint_as_float(b), &e);                 // |d| = m * 2^e, m in [0.5, 1)
+    return ldexp(1.0, 40 - e);
+}
+
+__device__ __forceinline__ void det_add(unsigned long long *a, long long v)
+{
+    atomicAdd(a, (unsigned long long)v);            // two's complement: negative contributions wrap correctly
+}
+
+__global__ void __launch_bounds__(256) splat_accumulate_det_kernel(const SplatParams p, unsigned long long *acc64,
+                                                                   const unsigned *maxbits)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int n = blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const int HW = p.H * p.W;
+    const int pix = y * p.W + x;
+    float X, Y;
+    bool zero;
+    endpoint(p, n, pix, x, y, X, Y, zero);
+    bool fm = !zero;                                                         // utils.py:1192
+    if (p.flow_mask) fm = fm && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix) != 0);
+    if (!fm) return;                                                         // weight * 0, utils.py:1123
+    const Corner2 k = make_corners(X, Y, p.H, p.W);
+    const bool is_bad = p.data_mask && (__ldg(p.data_mask + (int64_t)n * p.data_mask_bs + pix) == 0);
+    unsigned long long *acc = acc64 + (int64_t)n * (p.C + 2) * HW;
+    const float *data = p.data + (int64_t)n * p.data_bs + pix;
+    const double scale = det_scale(maxbits);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const float w = __fmul_rn(k.wy[a], k.wx[b]);                     // utils.py:1114
+            if (!(w > 0.0f)) continue;
+            const int q = p.W * k.Y[a] + k.X[b];                             // utils.py:1118
+            const long long wq = max(1ll, __double2ll_rn((double)w * 1099511627776.0));   // 2^40
+            det_add(acc + (int64_t)p.C * HW + q, wq);                        // utils.py:1133
+            if (is_bad) det_add(acc + (int64_t)(p.C + 1) * HW + q, wq);
+            for (int c = 0; c < p.C; ++c)                                    // utils.py:1139-1140
+                det_add(acc + (int64_t)c * HW + q, __double2ll_rn((double)w * (double)__ldg(data + (int64_t)c * HW) * scale));
+        }
+}
+
+__global__ void __launch_bounds__(256) splat_normalise_det_kernel(const SplatParams p, const unsigned long long *acc64,
+                                                                  const unsigned *maxbits)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int n = blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const int HW = p.H * p.W;
+    const int pix = y * p.W + x;
+    const unsigned long long *acc = acc64 + (int64_t)n * (p.C + 2) * HW + pix;
+    const double inv40 = 1.0 / 1099511627776.0, inv_scale = 1.0 / det_scale(maxbits);
+    const float den = (float)((double)(long long)acc[(int64_t)p.C * HW] * inv40);
+    const float bad = p.data_mask ? (float)((double)(long long)acc[(int64_t)(p.C + 1) * HW] * inv40) : 0.0f;
+    const float dc = fmaxf(den, OFB_MIN_DENSITY);
+    const bool wm = acc[(int64_t)p.C * HW] != 0ull;
+    bool unocc = false;
+    if (p.occlude_zero && p.relative && !wm) {
+        const float fx = __ldg(p.cx + (int64_t)n * p.coord_bs + pix);
+        const float fy = __ldg(p.cy + (int64_t)n * p.coord_bs + pix);
+        unocc = is_zero_vec(fx, fy);
+        if (p.flow_mask) unocc = unocc && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix) != 0);
+    }
+    const float *data = p.data + (int64_t)n * p.data_bs + pix;
+    float *out = p.out + (int64_t)n * p.C * HW + pix;
+    for (int c = 0; c < p.C; ++c) {
+        const float num = (float)((double)(long long)acc[(int64_t)c * HW] * inv_scale);
+        out[(int64_t)c * HW] = unocc ? __ldg(data + (int64_t)c * HW) : __fdiv_rn(num, dc);
+    }
+    if (p.density) p.density[(int64_t)n * HW + pix] = den;
+    if (p.warped_mask) p.warped_mask[(int64_t)n * HW + pix] = wm ? 1 : 0;
+    if (p.unocc) p.unocc[(int64_t)n * HW + pix] = unocc ? 1 : 0;
+    if (p.valid) {
+        float mch;
+        if (unocc) {
+            mch = (p.data_mask && __ldg(p.data_mask + (int64_t)n * p.data_mask_bs + pix) == 0) ? 0.0f : 1.0f;
+        } else {
+            const float mnum = (bad == 0.0f) ? den : __fsub_rn(den, bad);
+            mch = __fdiv_rn(mnum, dc);
+        }
+        const bool ok = (p.valid_mode == OFB_VALID_EQ1) ? (mch == 1.0f) : (mch > 0.99999f);
+        p.valid[(int64_t)n * HW + pix] = ok ? 1 : 0;
+    }
+}
+
+// floats of workspace the deterministic path needs: C + 2 int64 planes per item and the max|data| word
+static int64_t splat_det_floats(int N, int C, int H, int W) { return (int64_t)N * (C + 2) * H * W * 2 + 4; }
+
+// ------------------------------------------------------------------------------------------------
 // v1 forward: interleaved accumulators, vector REDs, register merging
 // ------------------------------------------------------------------------------------------------
 // The accumulator is this library's private workspace, so its layout is free: KP = 4 or 8 floats PER TARGET PIXEL
@@ -842,6 +961,7 @@ extern "C" int64_t ofb_splat_s_workspace(int N, int C, int H, int W, int has_dat
 {
     SplatV1 k;
     if (N <= 0 || C < 0 || H <= 0 || W <= 0) return 0;
+    if (g_splat_det) return splat_det_floats(N, C, H, W);        // also covers the fast path (it needs less)
     if (getenv("OFB_SPLAT_PLANAR") == nullptr && splat_v1(C, has_data_mask != 0, &k)) {
         int kp;
         bool split;
@@ -875,6 +995,25 @@ static int splat_fwd_impl(const float *cx, const float *cy, int64_t coord_bs, in
     SplatParams p{cx, cy, coord_bs, relative, sign, data, data_bs, data_mask, data_mask_bs,
                   flow_mask, flow_mask_bs, occlude_zero, acc, out, density, warped_mask, unocc,
                   valid, valid_mode, N, C, H, W, win[0], win[2], win[0], H, nullptr, win[1], win[3]};
+    if (g_splat_det && !windowed && acc_floats >= splat_det_floats(N, C, H, W) && aligned16(acc)) {
+        // deterministic merge: max|data| -> fixed-point accumulate -> normalise
+        unsigned long long *acc64 = reinterpret_cast<unsigned long long *>(acc);
+        unsigned *maxbits = reinterpret_cast<unsigned *>(acc + (int64_t)N * (C + 2) * H * W * 2);
+        cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)splat_det_floats(N, C, H, W), st);
+        if (e != cudaSuccess) return (int)e;
+        if (C > 0) {
+            const int64_t count = (int64_t)(data_bs == 0 ? 1 : N) * C * H * W;
+            absmax_kernel<<<148 * 8, 256, 0, st>>>(data, count, maxbits);
+            OFB_CHECK_LAUNCH();
+        }
+        const dim3 block(32, 8);
+        const dim3 grid((W + 31) / 32, (H + 7) / 8, N);
+        splat_accumulate_det_kernel<<<grid, block, 0, st>>>(p, acc64, maxbits);
+        OFB_CHECK_LAUNCH();
+        splat_normalise_det_kernel<<<grid, block, 0, st>>>(p, acc64, maxbits);
+        OFB_CHECK_LAUNCH();
+        return 0;
+    }
     SplatV1 k;
     static const bool planar_only = getenv("OFB_SPLAT_PLANAR") != nullptr;
     if (!planar_only && splat_v1(C, data_mask != nullptr, &k)) {

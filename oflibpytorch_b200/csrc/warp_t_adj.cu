@@ -29,6 +29,7 @@ namespace ofb {
 
 int g_bwd_impl = -1;        // tuning knob (ofb_set_option): -1 auto, 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA
 int g_bwd_band_rows = 24;   // output rows per warp task
+extern int g_splat_det;     // splat_s.cu: deterministic (fixed-point) splat merge
 
 constexpr int kRingWS = 64;                       // window columns
 constexpr int kRingRB = 16;                       // ring rows
@@ -358,10 +359,12 @@ int warp_t_bwd_ring_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStrea
 }  // namespace ofb
 
 // Tuning knobs (profiling sweeps; the defaults are the measured best).  key 1: W adjoint implementation
-// (-1 auto, 0 register-merge, 1 ring + RED flush, 2 ring + TMA reduce flush); key 2: output rows per warp task.
+// (-1 auto, 0 register-merge, 1 ring + RED flush, 2 ring + TMA reduce flush); key 2: output rows per warp task;
+// key 4: deterministic splat merge (64-bit fixed point) on/off.
 extern "C" int ofb_set_option(int key, int value)
 {
     if (key == 1) { ofb::g_bwd_impl = value; return 0; }
     if (key == 2) { ofb::g_bwd_band_rows = value; return 0; }
+    if (key == 4) { ofb::g_splat_det = value ? 1 : 0; return 0; }
     return OFB_EINVAL;
 }

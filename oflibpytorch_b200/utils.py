@@ -94,6 +94,14 @@ class validation(object):
         return False
 
 
+def set_deterministic(on: bool):
+    """Deterministic splat merge: the forward 's' path accumulates in 64-bit fixed point, so its float outputs are
+    bit-identical from run to run (integer addition does not care about the order of the atomics).  About 3x slower
+    than the default float atomics, whose results differ in the last bits between runs (masks never do)."""
+    from . import _native
+    _native.check(_native.lib().ofb_set_option(4, 1 if on else 0), "ofb_set_option")
+
+
 def _defer_finite_check(flags: torch.Tensor, error_string: str):
     if len(_PENDING) >= 4096:          # bounded: drop the oldest entries unchecked rather than grow without limit
         del _PENDING[:2048]

@@ -368,3 +368,35 @@ def test_run_to_run_determinism(ref):
             else:
                 scale = float(a.abs().max()) + 1e-12
                 assert float((a - b).abs().max()) <= 1e-5 * scale, 'output %d drifted between runs' % k
+
+
+def test_deterministic_splat_mode_is_bit_reproducible_and_within_tolerance():
+    """of.set_deterministic(True): the 's' forward accumulates in 64-bit fixed point -- float outputs bit-identical from
+    run to run (north_star: 'a deterministic global merge'), still within tolerance of the oracle, masks unchanged."""
+    from oracle import oracle as o
+    m = of()
+    n, h, w = 2, 157, 243
+    flow = smooth_flow(n, h, w, 9.0, 81)
+    img = torch.rand(n, 3, h, w, generator=gen(82)) * 7.0 - 2.0
+    fmask, tmask = holed_mask(n, h, w, 83), holed_mask(n, h, w, 84)
+    ref_out, ref_valid = o.OFlow(flow, 's', fmask).apply(img, tmask, return_valid_area=True)
+    ref_sw = o.OFlow(flow, 's', fmask).switch_ref()
+    fast = m.Flow(flow.cuda(), 's', fmask.cuda()).apply(img.cuda(), tmask.cuda(), return_valid_area=True)
+    m.set_deterministic(True)
+    try:
+        runs = []
+        for _ in range(4):
+            fl = m.Flow(flow.cuda(), 's', fmask.cuda())
+            out, valid = fl.apply(img.cuda(), tmask.cuda(), return_valid_area=True)
+            sw = fl.switch_ref()
+            runs.append((out, valid, sw.vecs, sw.mask))
+    finally:
+        m.set_deterministic(False)
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert torch.equal(a, b), 'deterministic mode changed between runs'
+    assert_close(runs[0][0], ref_out, 'deterministic apply s')
+    assert_mask_equal(runs[0][1], ref_valid, 'deterministic apply s valid')
+    assert_close(runs[0][2], ref_sw.vecs, 'deterministic switch_ref')
+    assert_mask_equal(runs[0][3], ref_sw.mask, 'deterministic switch_ref mask')
+    assert_mask_equal(runs[0][1], fast[1], 'deterministic vs default valid')
