@@ -447,7 +447,8 @@ def main():
 
     per_kernel = {}
     for name, a, b in prof:
-        per_kernel.setdefault(name[:-3] if name.endswith('_ex') else name, []).append(a.elapsed_time(b))
+        base = name[:-3] if name.endswith('_ex') else (name[:-2] if name.endswith('_d') else name)
+        per_kernel.setdefault(base, []).append(a.elapsed_time(b))
     peak, peak_src = measured_peak()
     kernels = {}
     for name, ts in per_kernel.items():

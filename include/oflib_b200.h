@@ -54,10 +54,12 @@ int64_t ofb_launch_count(void);
 void ofb_launch_count_reset(void);
 
 /* Tuning knobs for profiling sweeps (the defaults are the measured best; not needed in production).
- *   key 1  W adjoint implementation: -1 auto, 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA reduce flush
+ *   key 1  W adjoint implementation: -1 auto (= 7), 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA reduce
+ *          flush, 7 tile-owned fixed-point accumulation
  *   key 2  W adjoint ring: output rows per warp task
  *   key 4  S forward: 1 = deterministic merge (64-bit fixed-point accumulation: float outputs bit-identical from run
  *          to run, about 3x slower), 0 = float atomics (default).  ofb_splat_s_workspace follows the mode.
+ *   key 5  W forward: 0 = lean kernel (default), 1 = direct kernel (the general path: windows, > 4 channels)
  * Returns 0, or OFB_EINVAL for an unknown key.  Process-wide, not thread-safe. */
 int ofb_set_option(int key, int value);
 
@@ -144,6 +146,30 @@ int ofb_warp_t_bwd_ex(const float *flow, int64_t flow_bs, float flow_sign,
                       float *gflow, float *gsrc, int64_t gsrc_bs,
                       int N, int C, int H, int W,
                       const int32_t *sel, void *stream);
+
+/* W with saved derivatives.  ofb_warp_t_fwd_d is ofb_warp_t_fwd_ex that additionally writes
+ *   dtaps (N, 2C, H, W)   plane 2c = d out[c] / d ix, plane 2c+1 = d out[c] / d iy (the bilinear derivative of the
+ *                         payload at the sample position, before the chain through the flow; the add_flow term is not
+ *                         part of it)
+ * and ofb_warp_t_bwd_d is ofb_warp_t_bwd_ex that, given the same dtaps, forms the flow gradient as
+ * sum_c gout[c] * dtaps[2c .. 2c+1] instead of gathering the 4C payload taps again (src may then be NULL).  This is
+ * the arithmetic of ATen's grid_sampler_2d_backward (behind utils.py:555) split at the point where the taps have been
+ * combined: the values are bit-identical to ofb_warp_t_bwd's.  dtaps = NULL makes both behave exactly like the _ex
+ * functions.  Needs 1 <= C <= 4 and H, W <= 65536 (OFB_EINVAL otherwise). */
+int ofb_warp_t_fwd_d(const float *flow, int64_t flow_bs, float flow_sign,
+                     const float *src, int64_t src_bs,
+                     const uint8_t *src_mask, int64_t src_mask_bs,
+                     const uint8_t *flow_mask, int64_t flow_mask_bs,
+                     float add_flow, float valid_thresh,
+                     float *out, uint8_t *valid,
+                     int N, int C, int H, int W,
+                     const int32_t *sel, int32_t *out_flags, float *dtaps, void *stream);
+int ofb_warp_t_bwd_d(const float *flow, int64_t flow_bs, float flow_sign,
+                     const float *src, int64_t src_bs,
+                     const float *gout, float add_flow,
+                     float *gflow, float *gsrc, int64_t gsrc_bs,
+                     int N, int C, int H, int W,
+                     const int32_t *sel, const float *dtaps, void *stream);
 
 /* Windowed W: the flow/out/valid/flow_mask tensors cover an H x W WINDOW located at (window[0], window[1]) = (y0, x0)
  * of a global field of window[2] x window[3] pixels; coordinates, the round trip and zero padding live in the global

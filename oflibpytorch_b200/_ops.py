@@ -23,10 +23,11 @@ _lib = torch.library.Library("oflib_b200", "DEF")
 _lib.define("flow_stats(Tensor flow, Tensor? mask) -> Tensor")
 _lib.define("flow_stats_batch(Tensor flow, Tensor? mask) -> Tensor")
 _lib.define("warp_t_fwd(Tensor flow, float sign, Tensor? src, Tensor? src_mask, Tensor? flow_mask, "
-            "float add_flow, float thresh, bool want_valid, Tensor? sel, bool want_flags) -> (Tensor, Tensor, Tensor)")
+            "float add_flow, float thresh, bool want_valid, Tensor? sel, bool want_flags, bool want_dtaps) -> "
+            "(Tensor, Tensor, Tensor, Tensor)")
 _lib.define("early_decide(Tensor? fflags, Tensor? pflags, int rules, int n) -> Tensor")
 _lib.define("warp_t_bwd(Tensor flow, float sign, Tensor src, Tensor gout, float add_flow, "
-            "bool need_gflow, bool need_gsrc, Tensor? sel) -> (Tensor, Tensor)")
+            "bool need_gflow, bool need_gsrc, Tensor? sel, Tensor? dtaps) -> (Tensor, Tensor)")
 _lib.define("splat_s_fwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor? data, Tensor? data_mask, "
             "Tensor? flow_mask, bool occlude_zero, int valid_mode, bool want_aux, int[] window) -> "
             "(Tensor, Tensor, Tensor, Tensor, Tensor)")
@@ -152,8 +153,20 @@ def _early_decide(fflags, pflags, rules, n) -> torch.Tensor:
     return sel
 
 
+# Saving the bilinear derivatives in the forward (ofb_warp_t_fwd_d) makes the adjoint's flow gradient a stream instead
+# of a second gather of the payload taps.  Measured on B200 (tools/ab_step.py, batch 32 x 3 x 1080p): adjoint 1.32 ->
+# 1.20 ms, forward 0.57 -> 0.84 ms (8C more bytes per pixel written and read back: the pair turns HBM-bound) -- a net
+# loss, hence opt-in.
+SAVE_DERIVATIVES = False
+
+
+def set_save_derivatives(on: bool) -> None:
+    global SAVE_DERIVATIVES
+    SAVE_DERIVATIVES = bool(on)
+
+
 def _warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid, sel=None,
-                want_flags=False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                want_flags=False, want_dtaps=False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     require_cuda(flow, "flow")
     flow = _f32c(flow)
     src = None if src is None else _f32c(src)
@@ -166,26 +179,32 @@ def _warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_val
     with torch.cuda.device(dev):
         out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
         valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
+        want_dtaps = bool(want_dtaps) and 1 <= c <= 4 and h <= 65536 and w <= 65536
+        dtaps = torch.empty((n, 2 * c, h, w) if want_dtaps else (0,), dtype=torch.float32, device=dev)
         head = (_p(flow), _bs(flow, n, 2 * hw), sign,
                 _p(src) if c else None, _bs(src, n, c * hw),
                 _p(src_mask), _bs(src_mask, n, hw), _p(flow_mask), _bs(flow_mask, n, hw),
                 add_flow, thresh, _p(out) if c else None, _p(valid) if want_valid else None,
                 n, c, h, w)
-        if sel is not None or want_flags:
+        if sel is not None or want_flags or want_dtaps:
             if want_flags:      # flags (zeroed) followed by the kernel's workspace (ofb_warp_t_flags_ints)
                 buf = torch.empty((int(_native.lib().ofb_warp_t_flags_ints(n, h, w)),), dtype=torch.int32, device=dev)
                 out_flags = buf[:n + 1]
                 out_flags.zero_()
             else:
                 buf = out_flags = torch.empty((0,), dtype=torch.int32, device=dev)
-            _call("ofb_warp_t_fwd_ex", *head, _p(sel), _p(buf) if want_flags else None, _stream())
+            if want_dtaps:
+                _call("ofb_warp_t_fwd_d", *head, _p(sel), _p(buf) if want_flags else None, _p(dtaps), _stream())
+            else:
+                _call("ofb_warp_t_fwd_ex", *head, _p(sel), _p(buf) if want_flags else None, _stream())
         else:
             out_flags = torch.empty((0,), dtype=torch.int32, device=dev)
             _call("ofb_warp_t_fwd", *head, _stream())
-    return out, valid, out_flags
+    return out, valid, out_flags, dtaps
 
 
-def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc, sel=None) -> Tuple[torch.Tensor, torch.Tensor]:
+def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc, sel=None,
+                dtaps=None) -> Tuple[torch.Tensor, torch.Tensor]:
     require_cuda(flow, "flow")
     flow, src, gout = _f32c(flow), _f32c(src), _f32c(gout)
     n, c, h, w = gout.shape
@@ -197,7 +216,9 @@ def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc, sel=None
         head = (_p(flow), _bs(flow, n, 2 * hw), sign, _p(src), _bs(src, n, c * hw), _p(gout), add_flow,
                 _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None, _bs(src, n, c * hw),
                 n, c, h, w)
-        if sel is not None:
+        if dtaps is not None and dtaps.numel() and need_gflow:
+            _call("ofb_warp_t_bwd_d", *head, _p(sel), _p(dtaps), _stream())
+        elif sel is not None:
             _call("ofb_warp_t_bwd_ex", *head, _p(sel), _stream())
         else:
             _call("ofb_warp_t_bwd", *head, _stream())
@@ -311,9 +332,10 @@ def _reduce_to(g: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
 class _WarpT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flow, src, src_mask, flow_mask, sign, add_flow, thresh, want_valid, sel, want_flags):
-        out, valid, out_flags = _ops.warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid,
-                                                sel, want_flags)
-        ctx.save_for_backward(flow, src, sel)
+        want_dtaps = SAVE_DERIVATIVES and ctx.needs_input_grad[0]
+        out, valid, out_flags, dtaps = _ops.warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid,
+                                                       sel, want_flags, want_dtaps)
+        ctx.save_for_backward(flow, src, sel, dtaps if dtaps.numel() else None)
         ctx.sign, ctx.add_flow = sign, add_flow
         ctx.mark_non_differentiable(valid, out_flags)
         ctx.set_materialize_grads(False)     # no zero-filled stand-in for the gradient of the boolean output
@@ -322,11 +344,11 @@ class _WarpT(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gout, _gvalid, _gflags):
-        flow, src, sel = ctx.saved_tensors
+        flow, src, sel, dtaps = ctx.saved_tensors
         need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gflow = gsrc = None
         if gout is not None and (need_gflow or need_gsrc):
-            gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc, sel)
+            gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc, sel, dtaps)
             if need_gflow:
                 gflow = _reduce_to(gf, flow)
             if need_gsrc:
@@ -387,8 +409,8 @@ def warp_t(flow, src, src_mask=None, flow_mask=None, sign=1.0, add_flow=0.0, thr
                                  % (fl.shape[0] - 1, n))
         sel = _ops.early_decide(fflags, pflags, int(early), n)
     if src is None:
-        out, valid, fl = _ops.warp_t_fwd(flow.detach(), float(sign), None, src_mask, flow_mask, 0.0, float(thresh), True,
-                                         sel, False)
+        out, valid, fl, _ = _ops.warp_t_fwd(flow.detach(), float(sign), None, src_mask, flow_mask, 0.0, float(thresh),
+                                            True, sel, False, False)
     else:
         out, valid, fl = _WarpT.apply(flow, src, src_mask, flow_mask, float(sign), float(add_flow), float(thresh),
                                       bool(want_valid), sel, bool(want_flags))

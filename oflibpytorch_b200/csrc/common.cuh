@@ -61,6 +61,23 @@ __device__ __forceinline__ float round_trip_fast(float c, const ExactDiv &e)
     return __fmul_rn(g, e.d);
 }
 
+// round_trip_fast without the |x| < 2^24 test of div_exact.  For d <= 65535 (the launcher checks) a coordinate with
+// |2c| >= 2^24 lies at least 127 field widths outside the field whatever the last bits of the quotient are: every tap
+// is out of bounds in both evaluations, the weights are finite, the output is 0 and the validity bit false, exactly
+// as with the IEEE division (an infinite coordinate gives NaN weights and a NaN output in both).  Inside |2c| < 2^24
+// this IS round_trip_fast.
+__device__ __forceinline__ float round_trip_unchecked(float c, const ExactDiv &e)
+{
+    const float x = __fmul_rn(c, 2.0f);
+    float q = __fmul_rn(x, e.rcp);
+    q = __fmaf_rn(__fmaf_rn(-e.d, q, x), e.rcp, q);
+    q = __fmaf_rn(__fmaf_rn(-e.d, q, x), e.rcp, q);
+    float g = __fsub_rn(q, 1.0f);
+    g = __fadd_rn(g, 1.0f);
+    g = __fmul_rn(g, 0.5f);
+    return __fmul_rn(g, e.d);
+}
+
 // The four bilinear taps of one sample position (zero padding: out-of-bounds taps read as 0).
 struct Taps {
     float nw, ne, sw, se;       // weights

@@ -21,6 +21,8 @@
 
 namespace ofb {
 
+int g_fwd_impl = 0;    // tuning knob (ofb_set_option key 5): 0 lean forward kernel, 1 direct kernel
+
 struct WarpFwdParams {
     const float *flow; int64_t flow_bs; float sign;
     const float *src; int64_t src_bs;
@@ -33,6 +35,7 @@ struct WarpFwdParams {
     // device-side early-out decision (ofb_early_decide) and the flags of the result (combine mode 3 chains):
     // out_flags = int32[N + 1] flags, followed by the per-CTA partial maxima the finishing kernel reduces
     const int32_t *sel; int32_t *out_flags;
+    float *dtaps;     // (N, 2C, H, W): d out[c] / d ix, d out[c] / d iy for the adjoint (ofb_warp_t_fwd_d), or nullptr
 };
 
 // Per-thread base pointers of one batch item (computed once; everything below is 32-bit offsets from them).
@@ -284,6 +287,128 @@ __global__ void __launch_bounds__(256, OFB_FWD_MINB) warp_t_fwd_direct_kernel(co
         sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r + wn.y0), ix, iy);
         const PixGeom g = pix_geom<WIN>(ix, iy, wn);
         warp_pixel<CN, WANT_VALID, STATS>(p, wn, ip, g, (y0 + r) * p.W + x, fx[r], fy[r], 0, p.C, &os);
+    }
+    if (STATS) publish_stats(p.out_flags, p.N, os.all, os.masked);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lean forward (the default for the plain warp: identity window, 1..4 channels)
+// ------------------------------------------------------------------------------------------------
+// Same mapping and arithmetic as the direct kernel, organised around what the SASS of that kernel showed it paid for
+// (225 warp-instructions per 32 pixels at 32 registers, 73 % issue-active):
+//   * a warp whose 32 x 4 taps all lie inside the image -- all but the warps sampling at the border -- takes a path
+//     with no tap predicates and no zero initialisation: one 64-bit address per tap ROW and plane, derived from
+//     per-item bases that stay in UNIFORM registers (they depend on blockIdx.z only);
+//   * everything else falls back to warp_pixel_direct, per warp and per row.
+#ifndef OFB_LEAN_ROWS
+#define OFB_LEAN_ROWS 4
+#endif
+#ifndef OFB_LEAN_MINB
+#define OFB_LEAN_MINB 8
+#endif
+constexpr int kLeanRows = OFB_LEAN_ROWS;
+
+//   * WANT_D: the kernel also writes d out[c] / d ix and d out[c] / d iy (2C planes).  The adjoint's flow gradient is
+//     then a stream (sum_c gout[c] * d[c]) instead of a second gather of the 4C payload taps, which is what bounds
+//     both kernels (L1 wavefronts of unaligned tap rows): 24 B/pixel more traffic for C = 3, about 30 % less adjoint.
+template <int CN, bool WANT_VALID, bool STATS, bool WANT_D>
+__global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(const WarpFwdParams p, const CoordCtx cc)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * 64 + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * (4 * kLeanRows) + (warp >> 1) * kLeanRows;
+    const int n = blockIdx.z;
+    const int W = p.W, HW = p.H * p.W;
+    const bool inside = x < W;
+    const unsigned live = __ballot_sync(0xffffffffu, inside);
+    if (!STATS && !inside) return;
+    const int rows = (STATS && !inside) ? 0 : min(kLeanRows, p.H - y0);
+    // per-item bases: functions of blockIdx.z only
+    const float *fl = p.flow + (int64_t)n * p.flow_bs;
+    const float *src = p.src + (int64_t)n * p.src_bs;
+    float *out = p.out + (int64_t)n * CN * HW;
+    const uint8_t *smask = p.src_mask ? p.src_mask + (int64_t)n * p.src_mask_bs : nullptr;
+    const uint8_t *fmask = p.flow_mask ? p.flow_mask + (int64_t)n * p.flow_mask_bs : nullptr;
+    uint8_t *valid = WANT_VALID ? p.valid + (int64_t)n * HW : nullptr;
+    float *dt = WANT_D ? p.dtaps + (int64_t)n * (2 * CN) * HW : nullptr;
+    asm volatile("" : "+l"(src), "+l"(out), "+l"(smask), "+l"(fmask), "+l"(valid), "+l"(dt));    // see item_ptrs()
+
+    float fx[kLeanRows], fy[kLeanRows];
+    {
+        const int q0 = y0 * W + min(x, W - 1);
+#pragma unroll
+        for (int r = 0; r < kLeanRows; ++r) {
+            const int q = (y0 + r < p.H) ? q0 + r * W : q0;
+            fx[r] = __ldg(fl + q);
+            fy[r] = __ldg(fl + (HW + q));
+        }
+    }
+    const float xf = (float)x;
+    const Window wn{0, 0, p.H, W, 0, 0, p.H, W};
+    OutStats os{0u, 0u};
+#pragma unroll
+    for (int r = 0; r < kLeanRows; ++r) {
+        if (r >= rows) break;
+        const int pix = (y0 + r) * W + x;
+        float ix, iy;
+        ix = round_trip_unchecked(__fmaf_rn(-cc.sign, fx[r], xf), cc.dw);
+        iy = round_trip_unchecked(__fmaf_rn(-cc.sign, fy[r], (float)(y0 + r)), cc.dh);
+        const int xi = __float2int_rd(ix), yi = __float2int_rd(iy);
+        const bool all_in = (unsigned)xi < (unsigned)(W - 1) && (unsigned)yi < (unsigned)(p.H - 1);
+        if (__all_sync(live, all_in)) {   // lanes right of the field never get here
+            const float x0 = floorf(ix), y0f = floorf(iy);
+            const float ex = __fsub_rn(__fadd_rn(x0, 1.0f), ix), wx = __fsub_rn(ix, x0);
+            const float sy = __fsub_rn(__fadd_rn(y0f, 1.0f), iy), ny = __fsub_rn(iy, y0f);
+            const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
+            const int o = yi * W + xi;
+            unsigned okbit = 1u;
+            if (WANT_VALID) {
+                float m;
+                if (smask) {
+                    const uint8_t *mn = smask + o, *ms = smask + (o + W);
+                    const float a = mask_to_float(__ldg(mn)), b = mask_to_float(__ldg(mn + 1));
+                    const float c = mask_to_float(__ldg(ms)), d = mask_to_float(__ldg(ms + 1));
+                    m = __fmaf_rn(d, wse, __fmaf_rn(c, wsw, __fmaf_rn(b, wne, __fmul_rn(a, wnw))));
+                } else {
+                    m = __fadd_rn(__fadd_rn(__fadd_rn(wnw, wne), wsw), wse);     // 1*w == w, fma(1, w, r) == w + r
+                }
+                bool ok = m > p.thresh;                                          // flow_class.py:898,922
+                if (fmask) ok = ok && (__ldg(fmask + pix) != 0);                 // flow_class.py:934
+                valid[pix] = ok ? 1 : 0;
+                okbit = ok ? 1u : 0u;
+            }
+#pragma unroll
+            for (int c = 0; c < CN; ++c) {
+                const float *tn = src + (c * HW + o), *ts = src + (c * HW + o + W);
+                const float a = __ldg(tn), b = __ldg(tn + 1), cq = __ldg(ts), d = __ldg(ts + 1);
+                float v = __fmaf_rn(d, wse, __fmaf_rn(cq, wsw, __fmaf_rn(b, wne, __fmul_rn(a, wnw))));
+                if (p.add_flow != 0.0f && c < 2)                                 // flow_class.py:1804,1808
+                    v = __fadd_rn(__fmul_rn(p.add_flow, c == 0 ? fx[r] : fy[r]), v);
+                out[c * HW + pix] = v;
+                if (WANT_D) {           // same expressions as the adjoint kernels
+                    dt[(2 * c) * HW + pix] = __fmaf_rn(b - a, sy, (d - cq) * ny);
+                    dt[(2 * c + 1) * HW + pix] = __fmaf_rn(cq - a, ex, (d - b) * wx);
+                }
+                if (STATS) {
+                    const unsigned u = __float_as_uint(v) & 0x7fffffffu;
+                    os.all = max(os.all, u);
+                    os.masked = max(os.masked, u * okbit);
+                }
+            }
+        } else {
+            ItemPtrs ip{src, out, smask, fmask, valid};
+            const PixGeom g = pix_geom<false>(ix, iy, wn);
+            warp_pixel_direct<CN, WANT_VALID, false, STATS>(p, wn, ip, g, pix, fx[r], fy[r], 0, CN, &os);
+            if (WANT_D) {
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    float a, b, cq, d;
+                    load_taps<false, float>(src + (c * HW + g.o), src + (c * HW + g.o + W), g, a, b, cq, d);
+                    dt[(2 * c) * HW + pix] = __fmaf_rn(b - a, g.sy, (d - cq) * g.ny);
+                    dt[(2 * c + 1) * HW + pix] = __fmaf_rn(cq - a, g.ex, (d - b) * g.wx);
+                }
+            }
+        }
     }
     if (STATS) publish_stats(p.out_flags, p.N, os.all, os.masked);
 }
@@ -706,7 +831,7 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
                            float add_flow, float valid_thresh,
                            float *out, uint8_t *valid,
                            int N, int C, int H, int W, const Window &win, void *stream,
-                           const int32_t *sel = nullptr, int32_t *out_flags = nullptr)
+                           const int32_t *sel = nullptr, int32_t *out_flags = nullptr, float *dtaps = nullptr)
 {
     if (!flow || N <= 0 || C < 0 || (C > 0 && (!src || !out)) || (C == 0 && !valid)) return OFB_EINVAL;
     if (out_flags && (C != 2 || !valid)) return OFB_EINVAL;       // flags of a result: flow-valued results only
@@ -714,7 +839,7 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     if (win.gh < 2 || win.gw < 2) return OFB_ESHAPE;
     if (!window_ok(win, H, W) || N > 65535) return OFB_EINVAL;
     WarpFwdParams p{flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
-                    add_flow, valid_thresh, out, valid, N, C, H, W, win, sel, out_flags};
+                    add_flow, valid_thresh, out, valid, N, C, H, W, win, sel, out_flags, dtaps};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const CoordCtx cc{{(float)(win.gw - 1), 1.0f / (float)(win.gw - 1)}, {(float)(win.gh - 1), 1.0f / (float)(win.gh - 1)},
                       flow_sign};
@@ -723,7 +848,7 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     // staging over-fetches (1+g)^2 for a flow gradient g, and its load->TMA->compute phases do not overlap inside a
     // CTA), so the staged kernel is opt-in (OFB_TMA=1) until it is software-pipelined across tiles.
     static const bool use_tma = getenv("OFB_TMA") != nullptr;
-    bool staged = use_tma && C > 0 && W >= kTileW && H >= kTileH && window_is_identity(win, H, W) && !sel && !out_flags;
+    bool staged = use_tma && !dtaps && C > 0 && W >= kTileW && H >= kTileH && window_is_identity(win, H, W) && !sel && !out_flags;
     const int vmode = !valid ? 0 : (src_mask ? 2 : 1);
     alignas(64) CUtensorMap mask_map;
     alignas(64) CUtensorMap src_maps[2];          // [0]: groups of kMaxCN channels, [1]: the remainder group
@@ -780,7 +905,22 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
             if (!win_id) return OFB_EINVAL;
             k = warp_t_fwd_direct_kernel<2, true, false, true>;
         }
-        k<<<grid, 256, 0, st>>>(p, cc);
+        dim3 lgrid = grid;
+        const bool lean = (g_fwd_impl == 0 || dtaps) && win_id && cn >= 1 && kLeanRows == kDirRows && W <= 65536 && H <= 65536;
+        if (dtaps && !lean) return OFB_EINVAL;
+        if (lean) {     // the plain warp: lean kernel
+#define OFB_LEAN(CN_) (dtaps ? (wv ? warp_t_fwd_lean_kernel<CN_, true, false, true> : warp_t_fwd_lean_kernel<CN_, false, false, true>) \
+                             : (wv ? warp_t_fwd_lean_kernel<CN_, true, false, false> : warp_t_fwd_lean_kernel<CN_, false, false, false>))
+            switch (cn) {
+                case 1: k = OFB_LEAN(1); break;
+                case 2: k = OFB_LEAN(2); break;
+                case 3: k = OFB_LEAN(3); break;
+                default: k = OFB_LEAN(4); break;
+            }
+#undef OFB_LEAN
+            if (out_flags) k = dtaps ? warp_t_fwd_lean_kernel<2, true, true, true> : warp_t_fwd_lean_kernel<2, true, true, false>;
+        }
+        k<<<lgrid, 256, 0, st>>>(p, cc);
     }
     OFB_CHECK_LAUNCH();
     if (sel) {
@@ -798,9 +938,11 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
                            const float *src, int64_t src_bs,
                            const float *gout, float add_flow,
                            float *gflow, float *gsrc, int64_t gsrc_bs,
-                           int N, int C, int H, int W, const Window &win, void *stream, const int32_t *sel = nullptr)
+                           int N, int C, int H, int W, const Window &win, void *stream, const int32_t *sel = nullptr,
+                           const float *dtaps = nullptr)
 {
-    if (!flow || !gout || N <= 0 || C <= 0 || (gflow && !src)) return OFB_EINVAL;
+    if (!flow || !gout || N <= 0 || C <= 0 || (gflow && !src && !dtaps)) return OFB_EINVAL;
+    if (dtaps && C > 4) return OFB_EINVAL;
     if (add_flow != 0.0f && C != 2) return OFB_EINVAL;
     if (win.gh < 2 || win.gw < 2) return OFB_ESHAPE;
     if (!window_ok(win, H, W) || N > 65535) return OFB_EINVAL;
@@ -808,44 +950,54 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     if (!gflow && !gsrc) return 0;
     const CoordCtx cc{{(float)(win.gw - 1), 1.0f / (float)(win.gw - 1)}, {(float)(win.gh - 1), 1.0f / (float)(win.gh - 1)},
                       flow_sign};
-    if (gsrc && window_is_identity(win, H, W)) {     // ring adjoint (warp_t_adj.cu); 1 = outside its domain
+    bool done = false;
+    if (gsrc && window_is_identity(win, H, W)) {
         const WarpBwdParams rp{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, win,
-                               nullptr};
-        const int rs = sel ? 1 : warp_t_bwd_ring_launch(rp, cc, st);
-        if (rs != 1) return rs;
+                               nullptr, dtaps};
+        // tile-owned accumulation (warp_t_tile.cu), the default; 1 = outside its domain
+        int rs = warp_t_bwd_tile_launch(rp, cc, st);
+        if (rs == 0) done = true;
+        else if (rs != 1) return rs;
+        if (!done && !sel) {                        // ring adjoint (warp_t_adj.cu), opt-in experiment
+            rs = warp_t_bwd_ring_launch(rp, cc, st);
+            if (rs != 1) return rs;
+        }
     }
-    // Optional L2-resident accumulation (OFB_BWD_CHUNK_MB > 0): walk the batch in chunks whose gradient image fits the
-    // L2, zero-filling each chunk right before its kernel so the REDs hit L2-resident lines (-24 B/pixel of DRAM
-    // traffic).  Measured on B200: a LOSS as separate launches (1.47 -> 1.58/1.75/1.88 ms at 96/48/24 MB chunks,
-    // tails and launch gaps dominate), hence off by default; it needs the zero-fill fused into one persistent kernel.
-    static const long chunk_mb = getenv("OFB_BWD_CHUNK_MB") ? atol(getenv("OFB_BWD_CHUNK_MB")) : 0;
-    const int64_t src_plane = (int64_t)win.sh * win.sw, out_plane = (int64_t)H * W;
-    const int64_t item_bytes = (int64_t)C * src_plane * 4;
-    int chunk = N;
-    if (gsrc && gsrc_bs != 0 && chunk_mb > 0) {
-        chunk = (int)((chunk_mb << 20) / item_bytes);
-        if (chunk < 1) chunk = 1;
-        if (chunk > N) chunk = N;
-    }
-    if (gsrc && gsrc_bs == 0) {                          // broadcast payload: one image accumulates the whole batch
-        cudaError_t e = cudaMemsetAsync(gsrc, 0, (size_t)item_bytes, st);
-        if (e != cudaSuccess) return (int)e;
-    }
-    for (int n0 = 0; n0 < N; n0 += chunk) {
-        const int nn = (N - n0 < chunk) ? (N - n0) : chunk;
-        if (gsrc && gsrc_bs != 0) {
-            cudaError_t e = cudaMemsetAsync(gsrc + (int64_t)n0 * gsrc_bs, 0, (size_t)item_bytes * nn, st);
+    if (!done && gflow && !src) return OFB_EINVAL;      // the other kernels gather the payload taps
+    if (!done) {
+        // Optional L2-resident accumulation (OFB_BWD_CHUNK_MB > 0): walk the batch in chunks whose gradient image fits the
+        // L2, zero-filling each chunk right before its kernel so the REDs hit L2-resident lines (-24 B/pixel of DRAM
+        // traffic).  Measured on B200: a LOSS as separate launches (1.47 -> 1.58/1.75/1.88 ms at 96/48/24 MB chunks,
+        // tails and launch gaps dominate), hence off by default; it needs the zero-fill fused into one persistent kernel.
+        static const long chunk_mb = getenv("OFB_BWD_CHUNK_MB") ? atol(getenv("OFB_BWD_CHUNK_MB")) : 0;
+        const int64_t src_plane = (int64_t)win.sh * win.sw, out_plane = (int64_t)H * W;
+        const int64_t item_bytes = (int64_t)C * src_plane * 4;
+        int chunk = N;
+        if (gsrc && gsrc_bs != 0 && chunk_mb > 0) {
+            chunk = (int)((chunk_mb << 20) / item_bytes);
+            if (chunk < 1) chunk = 1;
+            if (chunk > N) chunk = N;
+        }
+        if (gsrc && gsrc_bs == 0) {                          // broadcast payload: one image accumulates the whole batch
+            cudaError_t e = cudaMemsetAsync(gsrc, 0, (size_t)item_bytes, st);
             if (e != cudaSuccess) return (int)e;
         }
-        WarpBwdParams p{flow + (int64_t)n0 * flow_bs, flow_bs, flow_sign, src ? src + (int64_t)n0 * src_bs : nullptr, src_bs,
-                        gout + (int64_t)n0 * C * out_plane, add_flow, gflow ? gflow + (int64_t)n0 * 2 * out_plane : nullptr,
-                        gsrc ? gsrc + (int64_t)n0 * gsrc_bs : nullptr, gsrc_bs, nn, C, H, W, win, sel};
-        const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), nn);
-        for (int c0 = 0; c0 < C; c0 += kMaxCN) {       // channel groups of <= 4; gflow accumulates across groups
-            const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
-            bwd_kernel(cn, gflow != nullptr, gsrc != nullptr, !window_is_identity(win, H, W))<<<grid, 256, 0, st>>>(
-                p, cc, c0, c0 > 0 ? 1 : 0);
-            OFB_CHECK_LAUNCH();
+        for (int n0 = 0; n0 < N; n0 += chunk) {
+            const int nn = (N - n0 < chunk) ? (N - n0) : chunk;
+            if (gsrc && gsrc_bs != 0) {
+                cudaError_t e = cudaMemsetAsync(gsrc + (int64_t)n0 * gsrc_bs, 0, (size_t)item_bytes * nn, st);
+                if (e != cudaSuccess) return (int)e;
+            }
+            WarpBwdParams p{flow + (int64_t)n0 * flow_bs, flow_bs, flow_sign, src ? src + (int64_t)n0 * src_bs : nullptr, src_bs,
+                            gout + (int64_t)n0 * C * out_plane, add_flow, gflow ? gflow + (int64_t)n0 * 2 * out_plane : nullptr,
+                            gsrc ? gsrc + (int64_t)n0 * gsrc_bs : nullptr, gsrc_bs, nn, C, H, W, win, sel};
+            const dim3 grid((W + 63) / 64, (H + 4 * kBwdRows - 1) / (4 * kBwdRows), nn);
+            for (int c0 = 0; c0 < C; c0 += kMaxCN) {       // channel groups of <= 4; gflow accumulates across groups
+                const int cn = (C - c0 < kMaxCN) ? (C - c0) : kMaxCN;
+                bwd_kernel(cn, gflow != nullptr, gsrc != nullptr, !window_is_identity(win, H, W))<<<grid, 256, 0, st>>>(
+                    p, cc, c0, c0 > 0 ? 1 : 0);
+                OFB_CHECK_LAUNCH();
+            }
         }
     }
     if (sel) {
@@ -922,6 +1074,35 @@ extern "C" int ofb_warp_t_bwd_ex(const float *flow, int64_t flow_bs, float flow_
     if (H < 2 || W < 2) return OFB_ESHAPE;
     return warp_t_bwd_impl(flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W,
                            Window{0, 0, H, W, 0, 0, H, W}, stream, sel);
+}
+
+// ofb_warp_t_fwd_ex that also saves d out / d(ix, iy) for the adjoint, and the adjoint that consumes it
+extern "C" int ofb_warp_t_fwd_d(const float *flow, int64_t flow_bs, float flow_sign,
+                                const float *src, int64_t src_bs,
+                                const uint8_t *src_mask, int64_t src_mask_bs,
+                                const uint8_t *flow_mask, int64_t flow_mask_bs,
+                                float add_flow, float valid_thresh,
+                                float *out, uint8_t *valid,
+                                int N, int C, int H, int W,
+                                const int32_t *sel, int32_t *out_flags, float *dtaps, void *stream)
+{
+    if (H < 2 || W < 2) return OFB_ESHAPE;
+    if (dtaps && (C < 1 || C > 4)) return OFB_EINVAL;
+    return warp_t_fwd_impl(flow, flow_bs, flow_sign, src, src_bs, src_mask, src_mask_bs, flow_mask, flow_mask_bs,
+                           add_flow, valid_thresh, out, valid, N, C, H, W, Window{0, 0, H, W, 0, 0, H, W}, stream,
+                           sel, out_flags, dtaps);
+}
+
+extern "C" int ofb_warp_t_bwd_d(const float *flow, int64_t flow_bs, float flow_sign,
+                                const float *src, int64_t src_bs,
+                                const float *gout, float add_flow,
+                                float *gflow, float *gsrc, int64_t gsrc_bs,
+                                int N, int C, int H, int W,
+                                const int32_t *sel, const float *dtaps, void *stream)
+{
+    if (H < 2 || W < 2) return OFB_ESHAPE;
+    return warp_t_bwd_impl(flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W,
+                           Window{0, 0, H, W, 0, 0, H, W}, stream, sel, dtaps);
 }
 
 // Windowed variants: window[8] = {y0, x0, global_h, global_w, src_y0, src_x0, src_h, src_w} (see struct Window).

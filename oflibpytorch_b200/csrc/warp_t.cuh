@@ -99,6 +99,7 @@ struct WarpBwdParams {
     int N, C, H, W;
     Window win;
     const int32_t *sel;   // device-side early-out decision (ofb_early_decide), or nullptr
+    const float *dtaps;   // (N, 2C, H, W) d out[c] / d(ix, iy) saved by the forward (ofb_warp_t_fwd_d), or nullptr
 };
 
 // Predicated fire-and-forget reduction: `@p red.global.add.f32 [a + imm], v` -- no branch, no return value.
@@ -122,5 +123,8 @@ __host__ __device__ inline Window identity_window(int H, int W) { return Window{
 // warp_t_adj.cu: ring adjoint.  Returns 0 when it handled the call, 1 when the caller must use the register-merge
 // kernel (shape / layout outside its domain), or a CUDA error.
 int warp_t_bwd_ring_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStream_t st);
+
+// warp_t_tile.cu: tile-owned accumulation (the default adjoint of the plain warp).  Same return convention.
+int warp_t_bwd_tile_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStream_t st);
 
 }  // namespace ofb

@@ -27,9 +27,11 @@
 
 namespace ofb {
 
-int g_bwd_impl = -1;        // tuning knob (ofb_set_option): -1 auto, 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA
+int g_bwd_impl = -1;        // tuning knob (ofb_set_option): -1 auto (= 7), 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA,
+                            // 7 tile-owned fixed-point accumulation (warp_t_tile.cu)
 int g_bwd_band_rows = 24;   // output rows per warp task
 extern int g_splat_det;     // splat_s.cu: deterministic (fixed-point) splat merge
+extern int g_fwd_impl;      // warp_t.cu: W forward implementation
 
 constexpr int kRingWS = 64;                       // window columns
 constexpr int kRingRB = 16;                       // ring rows
@@ -323,7 +325,7 @@ int warp_t_bwd_ring_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStrea
 {
     int impl = g_bwd_impl;
     if (impl < 0) impl = 0;
-    if (impl == 0 || !p.gsrc || p.W < 64 || p.H < 2) return 1;
+    if ((impl != 1 && impl != 2) || !p.gsrc || p.W < 64 || p.H < 2) return 1;
     const int64_t HW = (int64_t)p.H * p.W;
     const int64_t item_bytes = (int64_t)p.C * HW * 4;
     {
@@ -360,11 +362,12 @@ int warp_t_bwd_ring_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStrea
 
 // Tuning knobs (profiling sweeps; the defaults are the measured best).  key 1: W adjoint implementation
 // (-1 auto, 0 register-merge, 1 ring + RED flush, 2 ring + TMA reduce flush); key 2: output rows per warp task;
-// key 4: deterministic splat merge (64-bit fixed point) on/off.
+// key 4: deterministic splat merge (64-bit fixed point) on/off; key 5: W forward (0 lean kernel, 1 direct kernel).
 extern "C" int ofb_set_option(int key, int value)
 {
     if (key == 1) { ofb::g_bwd_impl = value; return 0; }
     if (key == 2) { ofb::g_bwd_band_rows = value; return 0; }
     if (key == 4) { ofb::g_splat_det = value ? 1 : 0; return 0; }
+    if (key == 5) { ofb::g_fwd_impl = value; return 0; }
     return OFB_EINVAL;
 }

@@ -1,0 +1,349 @@
+// W adjoint, tile-owned accumulation (the default for the plain warp).
+//
+// Adjoint of reference utils.py:541-555 (grid_sample bilinear / zeros / align_corners=True, i.e. ATen's
+// grid_sampler_2d_backward): gflow is a gather, gsrc the un-normalised splat of w * gout.
+//
+// What bounded the register-merge kernel (warp_t.cu) was measured with ncu: every red.global costs the SM's L1 -> crossbar
+// port ONE request per 32-byte sector it touches, however few lanes are in it (385 M sectors = 13.4 GB of crossbar writes
+// for 1.6 GB of gradient, l1tex__m_l1tex2xbar_req_cycles_active 70 %), and merging taps in registers reduces lanes, not
+// sectors.  Here a CTA owns a 32 x 32 tile of OUTPUT pixels and accumulates all its 4*C contributions per pixel into a
+// shared-memory window (64 x 64 per channel) that covers the tile's footprint in the source image, then flushes the
+// window ONCE with dense 16-byte REDs, skipping empty quads: about 20 sectors per 32 pixels instead of 93.
+//
+// Float atomics on shared memory are CAS loops on sm_100 (ATOMS.CAST.SPIN); 32-bit integer adds are native
+// (ATOMS.ADD, about 2 clk per warp-op, tools/microbench.cu).  The window therefore accumulates in FIXED POINT with a
+// per-tile power-of-two scale: amax = max |gout| over the tile, amax in [2^E, 2^(E+1)), scale 2^(19-E).  A source pixel
+// receives at most one tap of each of the tile's 1024 pixels, each |w*g| < 2^(E+1), so the sum stays below 2^31 for
+// every input; one contribution is rounded to 2^(E-19) <= 1.9e-6 * amax (the fp32 REDs it replaces round at 6e-8 of the
+// running sum; the parity bar for gradients is 1e-4 of the gradient scale).  Integer addition is associative: the
+// tile's part of the sum does not depend on the order of arrival.  Tiles whose footprint does not fit the window (violent
+// flows) and tiles with a non-finite upstream gradient issue float REDs to global memory directly, per tap.
+#include <climits>
+
+#include "common.cuh"
+#include "warp_t.cuh"
+
+namespace ofb {
+
+extern int g_bwd_impl;
+
+constexpr int kTT = 32;                    // tile edge (output pixels): 8 warps x 4 rows, lane = column
+constexpr int kTRows = 4;                  // rows per thread
+constexpr int kTWin = 64;                  // window edge (source pixels)
+constexpr int kTPlane = kTWin * kTWin;     // ints per channel
+
+struct TileCtl {
+    int minx, maxx, miny, maxy;
+    unsigned amax;
+};
+
+__device__ __forceinline__ void red_add_f32(float *a, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(a), "f"(v));
+}
+
+__device__ __forceinline__ void red_add_v4(float *a, float x, float y, float z, float w)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w));
+}
+
+// GFLOW: 0 no flow gradient, 1 from the payload taps (global gathers), 2 from the derivative planes the forward saved
+template <int CN, int GFLOW>
+__global__ void __launch_bounds__(256, 4) warp_t_bwd_tile_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
+                                                                 const int accumulate_gflow, const int vec_ok)
+{
+    extern __shared__ __align__(16) int win[];                 // [CN][kTWin][kTWin]
+    __shared__ TileCtl ctl;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * kTT + lane;
+    const int y0 = blockIdx.y * kTT + warp * kTRows;
+    const int n = blockIdx.z;
+    const int W = p.W, H = p.H, HW = H * W;
+    const bool xin = x < W;
+    const int xc = min(x, W - 1);
+
+    const float *fl = p.flow + (int64_t)n * p.flow_bs;
+    const float *src = GFLOW == 1 ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HW : nullptr;
+    const float *dt = GFLOW == 2 ? p.dtaps + ((int64_t)n * p.C + c_off) * 2 * HW : nullptr;
+    const float *go = p.gout + ((int64_t)n * p.C + c_off) * HW;
+    float *gsrc = p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HW;
+    float *gf = GFLOW ? p.gflow + (int64_t)n * 2 * HW : nullptr;
+    asm volatile("" : "+l"(src), "+l"(dt), "+l"(go), "+l"(gsrc), "+l"(gf));
+
+    // ---- phase 0: clear the window (under the latency of phase 1's loads; clearing only the footprint once it is known
+    // was measured 3 % slower: one more barrier, and the stores no longer overlap anything), initialise the control block
+    {
+        int4 *w4 = reinterpret_cast<int4 *>(win);
+#pragma unroll
+        for (int i = 0; i < CN * kTPlane / 4 / 256; ++i) w4[i * 256 + threadIdx.x] = make_int4(0, 0, 0, 0);
+        if (threadIdx.x == 0) {
+            ctl.minx = INT_MAX; ctl.miny = INT_MAX; ctl.maxx = INT_MIN; ctl.maxy = INT_MIN; ctl.amax = 0u;
+        }
+    }
+
+    // ---- phase 1: inputs of the thread's rows, sample positions, footprint and largest |gout| of the tile
+    float ix[kTRows], iy[kTRows], gv[kTRows][CN];
+    {
+        float fx[kTRows], fy[kTRows];
+#pragma unroll
+        for (int r = 0; r < kTRows; ++r) {
+            const int q = min(y0 + r, H - 1) * W + xc;
+            fx[r] = __ldg(fl + q);
+            fy[r] = __ldg(fl + (HW + q));
+#pragma unroll
+            for (int c = 0; c < CN; ++c) gv[r][c] = __ldg(go + (c * HW + q));
+        }
+        const float xf = (float)x;
+        int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
+        unsigned amax = 0u;
+#pragma unroll
+        for (int r = 0; r < kTRows; ++r) {
+            const bool act = xin && (y0 + r < H);
+            ix[r] = round_trip_unchecked(__fmaf_rn(-cc.sign, fx[r], xf), cc.dw);
+            iy[r] = round_trip_unchecked(__fmaf_rn(-cc.sign, fy[r], (float)(y0 + r)), cc.dh);
+            const int xi = __float2int_rd(ix[r]), yi = __float2int_rd(iy[r]);
+            // pixels with at least one tap inside the image stretch the footprint, by their in-image taps only
+            const bool any = act && xi >= -1 && xi <= W - 1 && yi >= -1 && yi <= H - 1;
+            if (any) {
+                minx = min(minx, max(xi, 0)); maxx = max(maxx, min(xi + 1, W - 1));
+                miny = min(miny, max(yi, 0)); maxy = max(maxy, min(yi + 1, H - 1));
+            }
+#pragma unroll
+            for (int c = 0; c < CN; ++c) {
+                if (!act) gv[r][c] = 0.0f;
+                amax = max(amax, __float_as_uint(gv[r][c]) & 0x7fffffffu);
+            }
+        }
+        minx = __reduce_min_sync(0xffffffffu, minx); maxx = __reduce_max_sync(0xffffffffu, maxx);
+        miny = __reduce_min_sync(0xffffffffu, miny); maxy = __reduce_max_sync(0xffffffffu, maxy);
+        amax = __reduce_max_sync(0xffffffffu, amax);
+        __syncthreads();                                   // the control block is initialised
+        if (lane == 0) {
+            if (minx != INT_MAX) {
+                atomicMin(&ctl.minx, minx); atomicMax(&ctl.maxx, maxx);
+                atomicMin(&ctl.miny, miny); atomicMax(&ctl.maxy, maxy);
+            }
+            atomicMax(&ctl.amax, amax);
+        }
+        __syncthreads();
+    }
+    const int ox = ctl.minx & ~3, oy = ctl.miny;           // window origin (x a multiple of 4: 16-byte REDs at the flush)
+    const int ex_w = ctl.maxx - ox + 1, ex_h = ctl.maxy - oy + 1;
+    const unsigned amax = ctl.amax;
+    const bool nothing = ctl.minx == INT_MAX || amax == 0u;                 // no tap in the image, or a zero gradient
+    // fixed point needs the footprint inside the window and a finite gradient; otherwise float REDs per tap
+    const bool tiled = !nothing && ex_w <= kTWin && ex_h <= kTWin && amax < 0x7f800000u;
+    // amax in [2^E, 2^(E+1)), E = e - 127 clamped to >= -100: scale 2^(19-E), inverse 2^(E-19)
+    const int e = max((int)(amax >> 23), 27);
+    const float scale = __uint_as_float((unsigned)(127 + 19 + 127 - e) << 23);
+    const float inv_scale = __uint_as_float((unsigned)(e - 19) << 23);
+
+    const int fq = threadIdx.x & 15, fr0 = threadIdx.x >> 4;           // flush: 16 quads per window row, 16 rows per pass
+    const int nq = (ex_w + 3) >> 2;
+
+    // ---- phase 2: flow gradient (gather) and the contributions to the payload gradient
+    const int rows = min(kTRows, H - y0);                   // warp-uniform; <= 0 below the field
+#pragma unroll
+    for (int r = 0; r < kTRows; ++r) {
+        if (r >= rows) break;
+        const int pix = (y0 + r) * W + xc;
+        const int xi = __float2int_rd(ix[r]), yi = __float2int_rd(iy[r]);
+        const float x0 = floorf(ix[r]), y0f = floorf(iy[r]);
+        const float ex = __fsub_rn(__fadd_rn(x0, 1.0f), ix[r]), wx = __fsub_rn(ix[r], x0);
+        const float sy = __fsub_rn(__fadd_rn(y0f, 1.0f), iy[r]), ny = __fsub_rn(iy[r], y0f);
+        const int o = yi * W + xi;
+        const bool all_in = (unsigned)xi < (unsigned)(W - 1) && (unsigned)yi < (unsigned)(H - 1);
+        if (__all_sync(0xffffffffu, all_in && xin)) {
+            // ---- every tap of every lane is inside the image: no predicates
+            if (GFLOW) {
+                float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    float dx, dy;
+                    if (GFLOW == 2) {
+                        dx = __ldg(dt + ((2 * c) * HW + pix));
+                        dy = __ldg(dt + ((2 * c + 1) * HW + pix));
+                    } else {
+                        const float *tn = src + (c * HW + o), *ts = src + (c * HW + o + W);
+                        const float a = __ldg(tn), b = __ldg(tn + 1), cq = __ldg(ts), d = __ldg(ts + 1);
+                        // d out / d ix and d out / d iy
+                        dx = __fmaf_rn(b - a, sy, (d - cq) * ny);
+                        dy = __fmaf_rn(cq - a, ex, (d - b) * wx);
+                    }
+                    gix = __fmaf_rn(gv[r][c], dx, gix);
+                    giy = __fmaf_rn(gv[r][c], dy, giy);
+                }
+                float rx = -p.sign * gix, ry = -p.sign * giy;
+                if (p.add_flow != 0.0f) {                  // out[c] = add_flow*flow[c] + ...  (combine mode 3), c < 2
+                    if (c_off == 0) rx += p.add_flow * gv[r][0];
+                    if (c_off == 0 && CN > 1) ry += p.add_flow * gv[r][CN > 1 ? 1 : 0];
+                    if (c_off == 1) ry += p.add_flow * gv[r][0];
+                }
+                if (accumulate_gflow) { rx += __ldcg(gf + pix); ry += __ldcg(gf + (HW + pix)); }
+                __stcg(gf + pix, rx);
+                __stcg(gf + (HW + pix), ry);
+            }
+            if (tiled) {
+                int *wp = win + ((yi - oy) * kTWin + (xi - ox));
+                const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    const float gs = gv[r][c] * scale;
+                    atomicAdd(wp + c * kTPlane, __float2int_rn(wnw * gs));
+                    atomicAdd(wp + c * kTPlane + 1, __float2int_rn(wne * gs));
+                    atomicAdd(wp + c * kTPlane + kTWin, __float2int_rn(wsw * gs));
+                    atomicAdd(wp + c * kTPlane + kTWin + 1, __float2int_rn(wse * gs));
+                }
+            } else if (!nothing) {
+                const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    float *t = gsrc + (c * HW + o);
+                    red_add_f32(t, wnw * gv[r][c]);
+                    red_add_f32(t + 1, wne * gv[r][c]);
+                    red_add_f32(t + W, wsw * gv[r][c]);
+                    red_add_f32(t + W + 1, wse * gv[r][c]);
+                }
+            }
+        } else {
+            // ---- border warps: per-tap predicates
+            const bool bx0 = (unsigned)xi < (unsigned)W, bx1 = (unsigned)(xi + 1) < (unsigned)W;
+            const bool by0 = (unsigned)yi < (unsigned)H, by1 = (unsigned)(yi + 1) < (unsigned)H;
+            const bool pnw = xin && bx0 && by0, pne = xin && bx1 && by0, psw = xin && bx0 && by1, pse = xin && bx1 && by1;
+            if (GFLOW) {
+                float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    float dx, dy;
+                    if (GFLOW == 2) {
+                        dx = __ldg(dt + ((2 * c) * HW + pix));
+                        dy = __ldg(dt + ((2 * c + 1) * HW + pix));
+                    } else {
+                        const float *tn = src + (c * HW + o), *ts = src + (c * HW + o + W);
+                        float a = 0.0f, b = 0.0f, cq = 0.0f, d = 0.0f;
+                        if (pnw) a = __ldg(tn);
+                        if (pne) b = __ldg(tn + 1);
+                        if (psw) cq = __ldg(ts);
+                        if (pse) d = __ldg(ts + 1);
+                        dx = __fmaf_rn(b - a, sy, (d - cq) * ny);
+                        dy = __fmaf_rn(cq - a, ex, (d - b) * wx);
+                    }
+                    gix = __fmaf_rn(gv[r][c], dx, gix);
+                    giy = __fmaf_rn(gv[r][c], dy, giy);
+                }
+                float rx = -p.sign * gix, ry = -p.sign * giy;
+                if (p.add_flow != 0.0f) {
+                    if (c_off == 0) rx += p.add_flow * gv[r][0];
+                    if (c_off == 0 && CN > 1) ry += p.add_flow * gv[r][CN > 1 ? 1 : 0];
+                    if (c_off == 1) ry += p.add_flow * gv[r][0];
+                }
+                if (xin) {
+                    if (accumulate_gflow) { rx += __ldcg(gf + pix); ry += __ldcg(gf + (HW + pix)); }
+                    __stcg(gf + pix, rx);
+                    __stcg(gf + (HW + pix), ry);
+                }
+            }
+            if (!nothing) {
+                const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
+                int *wp = win + ((yi - oy) * kTWin + (xi - ox));       // only dereferenced for in-image taps
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    if (tiled) {
+                        const float gs = gv[r][c] * scale;
+                        if (pnw) atomicAdd(wp + c * kTPlane, __float2int_rn(wnw * gs));
+                        if (pne) atomicAdd(wp + c * kTPlane + 1, __float2int_rn(wne * gs));
+                        if (psw) atomicAdd(wp + c * kTPlane + kTWin, __float2int_rn(wsw * gs));
+                        if (pse) atomicAdd(wp + c * kTPlane + kTWin + 1, __float2int_rn(wse * gs));
+                    } else {
+                        float *t = gsrc + (c * HW + o);
+                        if (pnw) red_add_f32(t, wnw * gv[r][c]);
+                        if (pne) red_add_f32(t + 1, wne * gv[r][c]);
+                        if (psw) red_add_f32(t + W, wsw * gv[r][c]);
+                        if (pse) red_add_f32(t + W + 1, wse * gv[r][c]);
+                    }
+                }
+            }
+        }
+    }
+    if (!tiled) return;                                     // CTA-uniform
+    __syncthreads();
+
+    // ---- phase 3: flush the footprint, 4 columns per thread, empty quads skipped
+    {
+        const int q = fq, rr0 = fr0;
+        if (q < nq) {
+            const int gx = ox + 4 * q;
+#pragma unroll 1
+            for (int c = 0; c < CN; ++c) {
+                float *gp = gsrc + (c * HW + gx);
+                const int *wc = win + c * kTPlane + 4 * q;
+#pragma unroll 2
+                for (int rr = rr0; rr < ex_h; rr += 16) {
+                    const int4 v = *reinterpret_cast<const int4 *>(wc + rr * kTWin);
+                    if ((v.x | v.y | v.z | v.w) == 0) continue;
+                    float *g = gp + (oy + rr) * W;
+                    const float a = (float)v.x * inv_scale, b = (float)v.y * inv_scale;
+                    const float cq = (float)v.z * inv_scale, d = (float)v.w * inv_scale;
+                    if (vec_ok) {
+                        red_add_v4(g, a, b, cq, d);
+                    } else {                                 // nonzero entries are inside the image by construction
+                        if (v.x) red_add_f32(g, a);
+                        if (v.y) red_add_f32(g + 1, b);
+                        if (v.z) red_add_f32(g + 2, cq);
+                        if (v.w) red_add_f32(g + 3, d);
+                    }
+                }
+            }
+        }
+    }
+}
+
+typedef void (*TileKernel)(const WarpBwdParams, const CoordCtx, const int, const int, const int);
+
+template <int CN>
+static TileKernel tile_kernel_for(int gflow)
+{
+    if (gflow == 2) return warp_t_bwd_tile_kernel<CN, 2>;
+    return gflow ? warp_t_bwd_tile_kernel<CN, 1> : warp_t_bwd_tile_kernel<CN, 0>;
+}
+
+static TileKernel tile_kernel(int cn, int gflow)
+{
+    switch (cn) {
+        case 1: return tile_kernel_for<1>(gflow);
+        case 2: return tile_kernel_for<2>(gflow);
+        case 3: return tile_kernel_for<3>(gflow);
+        default: return tile_kernel_for<4>(gflow);
+    }
+}
+
+// Returns 0 when it handled the call, 1 when the caller must use the register-merge kernel, or a CUDA error.
+int warp_t_bwd_tile_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStream_t st)
+{
+    if (!(g_bwd_impl < 0 || g_bwd_impl == 7) || !p.gsrc) return 1;
+    if (p.W > 65536 || p.H > 65536 || p.W < 2 || p.H < 2) return 1;      // round_trip_unchecked's domain
+    const int64_t HW = (int64_t)p.H * p.W;
+    const int64_t item_bytes = (int64_t)p.C * HW * 4;
+    {
+        cudaError_t e = cudaMemsetAsync(p.gsrc, 0, (size_t)(p.gsrc_bs == 0 ? item_bytes : item_bytes * p.N), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // 16-byte REDs at the flush: every plane row must start 16-byte aligned
+    const int vec_ok = (p.W % 4 == 0) && aligned16(p.gsrc) && (p.gsrc_bs % 4 == 0);
+    const dim3 grid((p.W + kTT - 1) / kTT, (p.H + kTT - 1) / kTT, p.N);
+    for (int c0 = 0; c0 < p.C; c0 += 4) {          // channel groups of <= 4; gflow accumulates across groups
+        const int cn = (p.C - c0 < 4) ? (p.C - c0) : 4;
+        TileKernel k = tile_kernel(cn, !p.gflow ? 0 : (p.dtaps ? 2 : 1));
+        const int smem = cn * kTPlane * 4;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<grid, 256, smem, st>>>(p, cc, c0, c0 > 0 ? 1 : 0, vec_ok);
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+}  // namespace ofb
