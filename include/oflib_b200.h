@@ -155,7 +155,10 @@ int ofb_warp_t_bwd_ex(const float *flow, int64_t flow_bs, float flow_sign,
  * sum_c gout[c] * dtaps[2c .. 2c+1] instead of gathering the 4C payload taps again (src may then be NULL).  This is
  * the arithmetic of ATen's grid_sampler_2d_backward (behind utils.py:555) split at the point where the taps have been
  * combined: the values are bit-identical to ofb_warp_t_bwd's.  dtaps = NULL makes both behave exactly like the _ex
- * functions.  Needs 1 <= C <= 4 and H, W <= 65536 (OFB_EINVAL otherwise). */
+ * functions.  Needs 1 <= C <= 4 and H, W <= 65536 (OFB_EINVAL otherwise).
+ * gout_broadcast = 1: gout points at ONE float that stands for the whole (N, C, H, W) upstream gradient -- what
+ * autograd hands down for out.sum() as a stride-0 view -- and is never materialised (needs the
+ * default adjoint kernel; OFB_EINVAL otherwise, the caller then passes a dense gout). */
 int ofb_warp_t_fwd_d(const float *flow, int64_t flow_bs, float flow_sign,
                      const float *src, int64_t src_bs,
                      const uint8_t *src_mask, int64_t src_mask_bs,
@@ -169,7 +172,7 @@ int ofb_warp_t_bwd_d(const float *flow, int64_t flow_bs, float flow_sign,
                      const float *gout, float add_flow,
                      float *gflow, float *gsrc, int64_t gsrc_bs,
                      int N, int C, int H, int W,
-                     const int32_t *sel, const float *dtaps, void *stream);
+                     const int32_t *sel, const float *dtaps, int gout_broadcast, void *stream);
 
 /* Windowed W: the flow/out/valid/flow_mask tensors cover an H x W WINDOW located at (window[0], window[1]) = (y0, x0)
  * of a global field of window[2] x window[3] pixels; coordinates, the round trip and zero padding live in the global

@@ -33,7 +33,7 @@ SIGNATURES = {
     'ofb_warp_t_fwd_ex': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P], _I),
     'ofb_warp_t_bwd_ex': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P], _I),
     'ofb_warp_t_fwd_d': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),
-    'ofb_warp_t_bwd_d': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P, _P], _I),
+    'ofb_warp_t_bwd_d': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     'ofb_warp_t_win_fwd': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P, _P], _I),
     'ofb_warp_t_win_bwd': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P], _I),
     'ofb_splat_s_workspace': ([_I, _I, _I, _I, _I], _L),
@@ -86,6 +86,9 @@ def lib():
             raise RuntimeError("oflibpytorch_b200: ABI version mismatch, rebuild the extension")
         _lib = handle
     return _lib
+
+
+OFB_EINVAL, OFB_ESHAPE = -1, -2     # include/oflib_b200.h
 
 
 def check(status: int, what: str):

@@ -53,6 +53,20 @@ def _call(name: str, *args):
     PROFILE.append((name, e0, e1))
 
 
+def _try_call(name: str, *args) -> int:
+    """_call that hands the status back instead of raising (for entry points with a documented OFB_EINVAL answer)."""
+    fn = getattr(_native.lib(), name)
+    if PROFILE is None:
+        return int(fn(*args))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    status = int(fn(*args))
+    e1.record()
+    if status == 0:
+        PROFILE.append((name, e0, e1))
+    return status
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -206,22 +220,37 @@ def _warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_val
 def _warp_t_bwd(flow, sign, src, gout, add_flow, need_gflow, need_gsrc, sel=None,
                 dtaps=None) -> Tuple[torch.Tensor, torch.Tensor]:
     require_cuda(flow, "flow")
-    flow, src, gout = _f32c(flow), _f32c(src), _f32c(gout)
+    flow, src = _f32c(flow), _f32c(src)
     n, c, h, w = gout.shape
     hw = h * w
     dev = flow.device
+    # the gradient of out.sum() arrives as a stride-0 view of one value: the default adjoint reads that value instead
+    # of a materialised (N, C, H, W) copy (100 MB per 4K frame)
+    bcast = (gout.dtype == torch.float32 and gout.numel() > 1 and all(st == 0 for st in gout.stride())
+             and need_gsrc and h <= 65536 and w <= 65536)
     with torch.cuda.device(dev):
         gflow = torch.empty((n, 2, h, w) if need_gflow else (0,), dtype=torch.float32, device=dev)
         gsrc = torch.empty(tuple(src.shape) if need_gsrc else (0,), dtype=torch.float32, device=dev)
-        head = (_p(flow), _bs(flow, n, 2 * hw), sign, _p(src), _bs(src, n, c * hw), _p(gout), add_flow,
-                _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None, _bs(src, n, c * hw),
-                n, c, h, w)
-        if dtaps is not None and dtaps.numel() and need_gflow:
-            _call("ofb_warp_t_bwd_d", *head, _p(sel), _p(dtaps), _stream())
+
+        def head(g):
+            return (_p(flow), _bs(flow, n, 2 * hw), sign, _p(src), _bs(src, n, c * hw), _p(g), add_flow,
+                    _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None, _bs(src, n, c * hw),
+                    n, c, h, w)
+
+        has_d = dtaps is not None and dtaps.numel() > 0 and need_gflow
+        if bcast:
+            status = _try_call("ofb_warp_t_bwd_d", *head(gout), _p(sel), _p(dtaps) if has_d else None, 1, _stream())
+            if status == 0:
+                return gflow, gsrc
+            if status != _native.OFB_EINVAL:     # OFB_EINVAL: another adjoint kernel is selected, it needs a dense gout
+                _native.check(status, "ofb_warp_t_bwd_d")
+        gout = _f32c(gout)
+        if has_d:
+            _call("ofb_warp_t_bwd_d", *head(gout), _p(sel), _p(dtaps), 0, _stream())
         elif sel is not None:
-            _call("ofb_warp_t_bwd_ex", *head, _p(sel), _stream())
+            _call("ofb_warp_t_bwd_ex", *head(gout), _p(sel), _stream())
         else:
-            _call("ofb_warp_t_bwd", *head, _stream())
+            _call("ofb_warp_t_bwd", *head(gout), _stream())
     return gflow, gsrc
 
 

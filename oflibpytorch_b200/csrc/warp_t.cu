@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(256) warp_bwd_early_kernel(const WarpBwdParams
         const float *go = p.gout + (int64_t)n * p.C * HW;
         float rx = 0.0f, ry = 0.0f;
         for (int c = 0; c < p.C; ++c) {
-            const float g = go[(int64_t)c * HW + pix];
+            const float g = p.gout_bcast ? p.gout[0] : go[(int64_t)c * HW + pix];
             if (p.gsrc && p.gsrc_bs != 0) p.gsrc[(int64_t)n * p.gsrc_bs + (int64_t)c * HW + pix] = (sel != 3) ? g : 0.0f;
             if (sel != 2 && c == 0) rx = p.add_flow * g;
             if (sel != 2 && c == 1) ry = p.add_flow * g;
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(256) warp_bwd_early_kernel(const WarpBwdParams
             for (int c = 0; c < p.C; ++c) {
                 float sum = 0.0f;
                 if (sel != 3)
-                    for (int m = 0; m < p.N; ++m) sum += p.gout[((int64_t)m * p.C + c) * HW + pix];
+                    for (int m = 0; m < p.N; ++m) sum += p.gout_bcast ? p.gout[0] : p.gout[((int64_t)m * p.C + c) * HW + pix];
                 p.gsrc[(int64_t)c * HW + pix] = sum;
             }
         }
@@ -939,7 +939,7 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
                            const float *gout, float add_flow,
                            float *gflow, float *gsrc, int64_t gsrc_bs,
                            int N, int C, int H, int W, const Window &win, void *stream, const int32_t *sel = nullptr,
-                           const float *dtaps = nullptr)
+                           const float *dtaps = nullptr, int gout_bcast = 0)
 {
     if (!flow || !gout || N <= 0 || C <= 0 || (gflow && !src && !dtaps)) return OFB_EINVAL;
     if (dtaps && C > 4) return OFB_EINVAL;
@@ -953,7 +953,7 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     bool done = false;
     if (gsrc && window_is_identity(win, H, W)) {
         const WarpBwdParams rp{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, win,
-                               nullptr, dtaps};
+                               nullptr, dtaps, gout_bcast};
         // tile-owned accumulation (warp_t_tile.cu), the default; 1 = outside its domain
         int rs = warp_t_bwd_tile_launch(rp, cc, st);
         if (rs == 0) done = true;
@@ -963,7 +963,7 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
             if (rs != 1) return rs;
         }
     }
-    if (!done && gflow && !src) return OFB_EINVAL;      // the other kernels gather the payload taps
+    if (!done && ((gflow && !src) || gout_bcast)) return OFB_EINVAL;      // the other kernels gather the payload taps and read a dense gout
     if (!done) {
         // Optional L2-resident accumulation (OFB_BWD_CHUNK_MB > 0): walk the batch in chunks whose gradient image fits the
         // L2, zero-filling each chunk right before its kernel so the REDs hit L2-resident lines (-24 B/pixel of DRAM
@@ -1002,7 +1002,7 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     }
     if (sel) {
         const WarpBwdParams p{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, win,
-                              sel};
+                              sel, nullptr, gout_bcast};
         warp_bwd_early_kernel<<<148 * 8, 256, 0, st>>>(p);
         OFB_CHECK_LAUNCH();
     }
@@ -1098,11 +1098,11 @@ extern "C" int ofb_warp_t_bwd_d(const float *flow, int64_t flow_bs, float flow_s
                                 const float *gout, float add_flow,
                                 float *gflow, float *gsrc, int64_t gsrc_bs,
                                 int N, int C, int H, int W,
-                                const int32_t *sel, const float *dtaps, void *stream)
+                                const int32_t *sel, const float *dtaps, int gout_broadcast, void *stream)
 {
     if (H < 2 || W < 2) return OFB_ESHAPE;
     return warp_t_bwd_impl(flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W,
-                           Window{0, 0, H, W, 0, 0, H, W}, stream, sel, dtaps);
+                           Window{0, 0, H, W, 0, 0, H, W}, stream, sel, dtaps, gout_broadcast ? 1 : 0);
 }
 
 // Windowed variants: window[8] = {y0, x0, global_h, global_w, src_y0, src_x0, src_h, src_w} (see struct Window).

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, 4) warp_t_bwd_tile_kernel(const WarpBwdPa
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
     const float *src = GFLOW == 1 ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HW : nullptr;
     const float *dt = GFLOW == 2 ? p.dtaps + ((int64_t)n * p.C + c_off) * 2 * HW : nullptr;
-    const float *go = p.gout + ((int64_t)n * p.C + c_off) * HW;
+    const float *go = p.gout_bcast ? p.gout : p.gout + ((int64_t)n * p.C + c_off) * HW;
     float *gsrc = p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HW;
     float *gf = GFLOW ? p.gflow + (int64_t)n * 2 * HW : nullptr;
     asm volatile("" : "+l"(src), "+l"(dt), "+l"(go), "+l"(gsrc), "+l"(gf));
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256, 4) warp_t_bwd_tile_kernel(const WarpBwdPa
             fx[r] = __ldg(fl + q);
             fy[r] = __ldg(fl + (HW + q));
 #pragma unroll
-            for (int c = 0; c < CN; ++c) gv[r][c] = __ldg(go + (c * HW + q));
+            for (int c = 0; c < CN; ++c) gv[r][c] = __ldg(go + (p.gout_bcast ? 0 : c * HW + q));
         }
         const float xf = (float)x;
         int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;

@@ -135,3 +135,25 @@ def test_saved_derivatives_give_the_same_gradients():
         res.append((a.grad, b.grad))
     assert torch.equal(res[2][0], res[3][0])
     assert_grad_close(res[3][1], res[2][1], 'payload flow gradient')
+
+
+def test_broadcast_upstream_gradient_is_not_materialised():
+    """out.sum().backward() hands the adjoint a stride-0 gradient; the default kernel reads the single value."""
+    import oflibpytorch_b200 as of
+    n, c, h, w = 2, 3, 70, 101
+    flow, img, _ = case(n, c, h, w, 61)
+    res = []
+    for impl in (0, 7):       # 0: register-merge kernel (dense gout, the bcast request answers OFB_EINVAL), 7: tile kernel
+        lib().ofb_set_option(1, impl)
+        f, i = flow.clone().requires_grad_(), img.clone().requires_grad_()
+        out, _v = of.Flow(f, 't').apply(i, return_valid_area=True)
+        (out.sum() * 0.75).backward()
+        res.append((f.grad, i.grad))
+    assert torch.equal(res[0][0], res[1][0])
+    assert_grad_close(res[1][1], res[0][1], 'image gradient')
+    g1 = torch.full((1,), 0.75, device=DEV).expand(n, c, h, w)
+    assert all(s == 0 for s in g1.stride())
+    gf, gs = ops()._warp_t_bwd(flow, 1.0, img, g1, 0.0, True, True)
+    gf2, gs2 = ops()._warp_t_bwd(flow, 1.0, img, g1.contiguous(), 0.0, True, True)
+    assert torch.equal(gf, gf2)
+    assert_grad_close(gs, gs2, 'image gradient, broadcast vs dense gout')
