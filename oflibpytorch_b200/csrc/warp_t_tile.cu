@@ -7,7 +7,7 @@
 // port ONE request per 32-byte sector it touches, however few lanes are in it (385 M sectors = 13.4 GB of crossbar writes
 // for 1.6 GB of gradient, l1tex__m_l1tex2xbar_req_cycles_active 70 %), and merging taps in registers reduces lanes, not
 // sectors.  Here a CTA owns a 32 x 32 tile of OUTPUT pixels and accumulates all its 4*C contributions per pixel into a
-// shared-memory window (64 x 64 per channel) that covers the tile's footprint in the source image, then flushes the
+// shared-memory window (56 x 56 per channel) that covers the tile's footprint in the source image, then flushes the
 // window ONCE with dense 16-byte REDs, skipping empty quads: about 20 sectors per 32 pixels instead of 93.
 //
 // Float atomics on shared memory are CAS loops on sm_100 (ATOMS.CAST.SPIN); 32-bit integer adds are native
@@ -29,7 +29,18 @@ extern int g_bwd_impl;
 
 constexpr int kTT = 32;                    // tile edge (output pixels): 8 warps x 4 rows, lane = column
 constexpr int kTRows = 4;                  // rows per thread
-constexpr int kTWin = 64;                  // window edge (source pixels)
+#ifndef OFB_TILE_WIN
+#define OFB_TILE_WIN 56
+#endif
+#ifndef OFB_TILE_MINB
+#define OFB_TILE_MINB 4
+#endif
+// Window edge (source pixels; a multiple of 4, at most 64).  32 x 32 tiles of the benchmark's flow field map to about
+// 37 x 37 +- 8 source pixels: 56 covers 99.5 % of them in 37 KB for three channels.  64 covered them all, but four
+// resident CTAs of 48 KB left the SM too little L1 for the tap gathers of the flow gradient (measured, 32 x 3 x 1080p:
+// 1.28 ms at 64, 1.06 at 56, 1.04 at 48 where 10 % of the tiles already take the float-RED fall-back; a window of
+// fixed capacity whose pitch follows the footprint: 1.10).
+constexpr int kTWin = OFB_TILE_WIN;
 constexpr int kTPlane = kTWin * kTWin;     // ints per channel
 
 struct TileCtl {
@@ -49,7 +60,7 @@ __device__ __forceinline__ void red_add_v4(float *a, float x, float y, float z, 
 
 // GFLOW: 0 no flow gradient, 1 from the payload taps (global gathers), 2 from the derivative planes the forward saved
 template <int CN, int GFLOW>
-__global__ void __launch_bounds__(256, 4) warp_t_bwd_tile_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
+__global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
                                                                  const int accumulate_gflow, const int vec_ok)
 {
     extern __shared__ __align__(16) int win[];                 // [CN][kTWin][kTWin]
@@ -76,7 +87,7 @@ __global__ void __launch_bounds__(256, 4) warp_t_bwd_tile_kernel(const WarpBwdPa
     {
         int4 *w4 = reinterpret_cast<int4 *>(win);
 #pragma unroll
-        for (int i = 0; i < CN * kTPlane / 4 / 256; ++i) w4[i * 256 + threadIdx.x] = make_int4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < CN * kTPlane / 4; i += 256) w4[i] = make_int4(0, 0, 0, 0);
         if (threadIdx.x == 0) {
             ctl.minx = INT_MAX; ctl.miny = INT_MAX; ctl.maxx = INT_MIN; ctl.maxy = INT_MIN; ctl.amax = 0u;
         }
