@@ -3,15 +3,22 @@
 // Replaces reference utils.py:541-555 (apply_flow ref 't': grid - flow, normalise_coords, grid_sample(bilinear,
 // zeros, align_corners=True)) and the mask tracking of Flow.apply (flow_class.py:896-898,922-934).
 //
-// Forward, staged variant (the fast path).  A CTA owns a 64x32 tile of OUTPUT pixels, lanes along x, 8 rows per
-// thread.  Phase 1 streams the tile's flow (coalesced, 16 loads in flight per thread) and reduces the bounding box
-// of all sample positions; phase 2 has one thread issue TMA box copies (cp.async.bulk.tensor.3d) of that source
-// region -- all payload channels and the byte mask -- into shared memory, the TMA unit zero-filling whatever lies
-// outside the image (= padding_mode='zeros'); phase 3 evaluates the 4 taps per channel as LDS [reg + imm] off ONE
-// address register per pixel: no bounds predicates, no 64-bit address arithmetic, one wavefront per tap load.
-// Tiles whose footprint exceeds the box (violent flows) take the direct path below, per tile.
+// Forward, three kernels (measured on B200, profiles/):
+//   lean    (default for the plain warp, 1..4 channels): one thread per output pixel, 4 rows per thread; a warp whose
+//           taps all lie inside the image takes a path without tap predicates; bit-identical to the direct kernel.
+//   direct  (the general path: windows for padded / row-band warps, more than 4 channels, validity only): taps
+//           through the read-only path with explicit bounds predicates.
+//   staged  (opt-in, OFB_TMA=1): a CTA streams its tile's flow, reduces the bounding box of the sample positions and
+//           has one thread issue TMA box copies (cp.async.bulk.tensor.3d) of that source region into shared memory,
+//           zero-filled outside the image by the TMA unit; taps are then LDS [reg + imm].  Parity-green but slower
+//           (0.42 of the HBM peak against 0.62): the box over-fetches and the load -> TMA -> compute phases of a CTA do
+//           not overlap.
+// All three are bounded by the L1 data pipe, not by HBM: a tap row of 32 lanes is an unaligned 128-byte span that
+// drifts over several image rows (7.3 sectors and 2.3 wavefronts per load on the benchmark's flow field), and
+// l1tex__data_pipe_lsu_wavefronts sits at 70 % of its peak whatever the instruction count (the lean kernel issues
+// 128 instead of 225 instructions per 32 pixels and takes the same time).
 //
-// Direct variant: one thread per output pixel, taps through the read-only path with explicit bounds predicates.
+// Adjoint: warp_t_tile.cu (default), the register-merge kernel below (windows, fall-back), warp_t_adj.cu (ring, opt-in).
 #include <climits>
 #include <cstdlib>
 

@@ -7,7 +7,7 @@
 // port ONE request per 32-byte sector it touches, however few lanes are in it (385 M sectors = 13.4 GB of crossbar writes
 // for 1.6 GB of gradient, l1tex__m_l1tex2xbar_req_cycles_active 70 %), and merging taps in registers reduces lanes, not
 // sectors.  Here a CTA owns a 32 x 32 tile of OUTPUT pixels and accumulates all its 4*C contributions per pixel into a
-// shared-memory window (56 x 56 per channel) that covers the tile's footprint in the source image, then flushes the
+// shared-memory window (64 x 52 per channel) that covers the tile's footprint in the source image, then flushes the
 // window ONCE with dense 16-byte REDs, skipping empty quads: about 20 sectors per 32 pixels instead of 93.
 //
 // Float atomics on shared memory are CAS loops on sm_100 (ATOMS.CAST.SPIN); 32-bit integer adds are native
@@ -29,19 +29,26 @@ extern int g_bwd_impl;
 
 constexpr int kTT = 32;                    // tile edge (output pixels): 8 warps x 4 rows, lane = column
 constexpr int kTRows = 4;                  // rows per thread
-#ifndef OFB_TILE_WIN
-#define OFB_TILE_WIN 56
-#endif
 #ifndef OFB_TILE_MINB
 #define OFB_TILE_MINB 4
 #endif
-// Window edge (source pixels; a multiple of 4, at most 64).  32 x 32 tiles of the benchmark's flow field map to about
-// 37 x 37 +- 8 source pixels: 56 covers 99.5 % of them in 37 KB for three channels.  64 covered them all, but four
-// resident CTAs of 48 KB left the SM too little L1 for the tap gathers of the flow gradient (measured, 32 x 3 x 1080p:
-// 1.28 ms at 64, 1.06 at 56, 1.04 at 48 where 10 % of the tiles already take the float-RED fall-back; a window of
-// fixed capacity whose pitch follows the footprint: 1.10).
-constexpr int kTWin = OFB_TILE_WIN;
-constexpr int kTPlane = kTWin * kTWin;     // ints per channel
+#ifndef OFB_TILE_WINH
+#define OFB_TILE_WINH 52
+#endif
+// Window geometry.  32 x 32 tiles of the benchmark's flow field map to about 37 x 37 +- 8 source pixels.
+//   pitch 64: a multiple of 32, so lanes on neighbouring source rows never share a bank (their columns differ by less
+//             than 32); a 56-wide window had 105 M bank-conflict wavefronts per launch, 25 per 32 pixels.
+//   52 rows:  covers 99 % of the tiles in 40 KB for three channels.  What matters is that four resident CTAs leave the
+//             SM enough L1 for the tap gathers of the flow gradient -- measured per 32 x 3 x 1080p launch: 64 x 64
+//             (48 KB) 1.28 ms, 56 x 56 1.06, 64 x 56 1.06, 64 x 52 1.03, 64 x 48 1.04, 64 x 44 1.06 (fall-backs grow);
+//             a window of fixed capacity whose pitch follows the footprint: 1.10.
+constexpr int kTWin = 64;                  // window row pitch (ints)
+constexpr int kTWinH = OFB_TILE_WINH;      // window rows
+constexpr int kTPlane = kTWin * kTWinH;    // ints per channel
+
+#ifndef OFB_TILE_LD
+#define OFB_TILE_LD __ldg
+#endif
 
 struct TileCtl {
     int minx, maxx, miny, maxy;
@@ -100,10 +107,10 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
 #pragma unroll
         for (int r = 0; r < kTRows; ++r) {
             const int q = min(y0 + r, H - 1) * W + xc;
-            fx[r] = __ldg(fl + q);
-            fy[r] = __ldg(fl + (HW + q));
+            fx[r] = OFB_TILE_LD(fl + q);
+            fy[r] = OFB_TILE_LD(fl + (HW + q));
 #pragma unroll
-            for (int c = 0; c < CN; ++c) gv[r][c] = __ldg(go + (p.gout_bcast ? 0 : c * HW + q));
+            for (int c = 0; c < CN; ++c) gv[r][c] = OFB_TILE_LD(go + (p.gout_bcast ? 0 : c * HW + q));
         }
         const float xf = (float)x;
         int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
     const unsigned amax = ctl.amax;
     const bool nothing = ctl.minx == INT_MAX || amax == 0u;                 // no tap in the image, or a zero gradient
     // fixed point needs the footprint inside the window and a finite gradient; otherwise float REDs per tap
-    const bool tiled = !nothing && ex_w <= kTWin && ex_h <= kTWin && amax < 0x7f800000u;
+    const bool tiled = !nothing && ex_w <= kTWin && ex_h <= kTWinH && amax < 0x7f800000u;
     // amax in [2^E, 2^(E+1)), E = e - 127 clamped to >= -100: scale 2^(19-E), inverse 2^(E-19)
     const int e = max((int)(amax >> 23), 27);
     const float scale = __uint_as_float((unsigned)(127 + 19 + 127 - e) << 23);

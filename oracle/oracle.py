@@ -2,7 +2,7 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this module.  The product package
-``oflibpytorch_b200`` never does (tests/test_no_oracle_in_product.py enforces it).
+``oflibpytorch_b200`` never does (tests/test_capi_symbols.py::test_product_never_imports_the_oracle enforces it).
 
 Parity status: PINNED against the unmodified reference (tests/test_oracle_pinned.py,
 golden vectors in tests/golden/ made by tests/golden/make_golden.py) and against the
