@@ -1,9 +1,11 @@
 """Parity at BASELINE.json's FULL sizes (configs 2, 3 and 4).  The oracle cannot run 64 x 1080p in seconds, so the
 full-size results are checked through properties that do not depend on the size:
 
-* batch independence + sampling: every batch item is independent, so a few items of the full-batch
-  result are compared with the ORACLE run on just those items -- masks bit-exact, W forward bit-exact, floats and
-  gradients within the tolerance of BASELINE.json;
+* batch independence: every batch item is independent, so the items of the full-batch result are
+  compared one by one with the ORACLE run on just that item -- ALL 64 items of config 2 (the headline), every fourth
+  item of config 3 -- masks bit-exact, W forward bit-exact, floats and gradients within the tolerance of BASELINE.json;
+* config 5 at full 4K resolution: a chain of four frames (combine_with mode 3 + apply + one backward) against the
+  oracle's chain;
 * the adjoint identity <A x, g> = <x, A^T g> ties each hand-written backward kernel to its forward at full size;
 * linearity in the payload;
 * integer / half-pixel translations (the adversarial cases for the mask bits) give every item the oracle's mask.
@@ -20,7 +22,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 pytestmark = pytest.mark.gpu
 
-SAMPLES = (0, 37, 63)
+SAMPLES = {'t': tuple(range(64)), 's': tuple(range(0, 32, 4)) + (31,)}
 
 
 def of():
@@ -50,7 +52,7 @@ def test_full_batch_items_match_the_oracle(ref, n):
     # adjoint identity over the whole batch, payload side: <A img, gout> = <img, A^T gout> (A is linear in img)
     lhs, rhs = dot(out.detach(), gout), dot(img, i.grad)
     assert abs(lhs - rhs) <= 1e-5 * abs(lhs), (lhs, rhs)
-    for k in [s for s in SAMPLES if s < n]:
+    for k in [s for s in SAMPLES[ref] if s < n]:
         fo, io = flow[k:k + 1].cpu().requires_grad_(), img[k:k + 1].cpu().requires_grad_()
         oo, vo = orc().OFlow(fo, ref, mask[k:k + 1].cpu()).apply(io, tmask[k:k + 1].cpu(), return_valid_area=True)
         oo.backward(gout[k:k + 1].cpu())
@@ -115,3 +117,45 @@ def test_full_size_integer_and_half_pixel_translations_match_the_oracle():
             fl, ofl = of().Flow(flow, ref), o.OFlow(one, ref)
             assert_mask_equal(fl.valid_target(), ofl.valid_target().expand(n, h, w), 'valid_target ' + ref)
             assert_mask_equal(fl.valid_source(), ofl.valid_source().expand(n, h, w), 'valid_source ' + ref)
+
+
+def test_config5_chain_at_4k_matches_the_oracle():
+    """config 5 (256-frame 4K chain) at full resolution, four frames: acc = acc.combine_with(f_i, 3); acc.apply(img) +
+    valid area; one backward through the chain (reference flow_class.py:1648-1810 + :755-959).  Deferred validation,
+    as the bench runs it."""
+    import bench
+    h, w, frames = 2160, 3840, 4
+    o = orc()
+    flows = [bench.smooth_flow(1, h, w, 4.0, 100 + i, 'cuda') for i in range(frames)]
+    img = torch.rand(1, 3, h, w, generator=torch.Generator(device='cuda').manual_seed(7), device='cuda')
+
+    def chain(mod, flow_cls, fl, im):
+        acc, loss, last = None, None, None
+        for f in fl:
+            cur = flow_cls(f, 't')
+            acc = cur if acc is None else acc.combine_with(cur, 3)
+            out, valid = acc.apply(im, return_valid_area=True)
+            loss = out.sum() if loss is None else loss + out.sum()
+            last = (out, valid, acc)
+        loss.backward()
+        return last
+
+    prev = of().get_validation()
+    of().set_validation('deferred')
+    try:
+        fl = [f.clone().requires_grad_() for f in flows]
+        im = img.clone().requires_grad_()
+        out, valid, acc = chain(of(), of().Flow, fl, im)
+        of().check_deferred()
+    finally:
+        of().set_validation(prev)
+    flo = [f.cpu().requires_grad_() for f in flows]
+    imo = img.cpu().requires_grad_()
+    oo, vo, acco = chain(o, o.OFlow, flo, imo)
+    assert_mask_equal(valid, vo, 'valid area of the last frame')
+    assert_mask_equal(acc.mask, acco.mask, 'mask of the accumulated flow')
+    assert_close(acc.vecs, acco.vecs, 'accumulated flow')
+    assert_close(out, oo, 'last warped image')
+    assert_grad_close(im.grad, imo.grad, 'image gradient through the chain')
+    for k in range(frames):
+        assert_grad_close(fl[k].grad, flo[k].grad, 'gradient of flow %d' % k)
