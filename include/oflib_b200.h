@@ -174,6 +174,24 @@ int ofb_warp_t_bwd_d(const float *flow, int64_t flow_bs, float flow_sign,
                      int N, int C, int H, int W,
                      const int32_t *sel, const float *dtaps, int gout_broadcast, void *stream);
 
+/* W with an INSET flow: flow (N|1, 2, fh, fw) and flow_mask (N|1, fh, fw) cover the window at (fwin[0], fwin[1]) =
+ * (y0, x0) of size fwin[2] x fwin[3] = fh x fw inside the H x W frame of src / out / valid; outside the window the flow
+ * is zero and valid is false.  Replaces Flow.apply(padding=..., cut=False) for 't' flows (reference
+ * flow_class.py:905-934: zero-pad the flow, warp the whole frame, keep the valid area inside the window only) without
+ * materialising the padded flow and mask; per pixel it is the arithmetic of ofb_warp_t_fwd, so the results are
+ * bit-identical to warping with the padded flow.  `fwin` is a HOST pointer to 4 ints.  The adjoint returns gflow of the
+ * window's size (the padded vectors are constants) and gsrc of the frame's size (zero-filled by the call). */
+int ofb_warp_t_inset_fwd(const float *flow, int64_t flow_bs,
+                         const float *src, int64_t src_bs,
+                         const uint8_t *src_mask, int64_t src_mask_bs,
+                         const uint8_t *flow_mask, int64_t flow_mask_bs,
+                         float valid_thresh, float *out, uint8_t *valid,
+                         int N, int C, int H, int W, const int *fwin, void *stream);
+int ofb_warp_t_inset_bwd(const float *flow, int64_t flow_bs,
+                         const float *src, int64_t src_bs,
+                         const float *gout, float *gflow, float *gsrc, int64_t gsrc_bs,
+                         int N, int C, int H, int W, const int *fwin, void *stream);
+
 /* Windowed W: the flow/out/valid/flow_mask tensors cover an H x W WINDOW located at (window[0], window[1]) = (y0, x0)
  * of a global field of window[2] x window[3] pixels; coordinates, the round trip and zero padding live in the global
  * frame.  src / src_mask / gsrc store rows [window[4], window[4]+window[6]) x cols [window[5], window[5]+window[7])

@@ -34,6 +34,8 @@ SIGNATURES = {
     'ofb_warp_t_bwd_ex': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P], _I),
     'ofb_warp_t_fwd_d': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     'ofb_warp_t_bwd_d': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P, _I, _P], _I),
+    'ofb_warp_t_inset_fwd': ([_P, _L, _P, _L, _P, _L, _P, _L, _F, _P, _P, _I, _I, _I, _I, _P, _P], _I),
+    'ofb_warp_t_inset_bwd': ([_P, _L, _P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _P, _P], _I),
     'ofb_warp_t_win_fwd': ([_P, _L, _F, _P, _L, _P, _L, _P, _L, _F, _F, _P, _P, _I, _I, _I, _I, _P, _P], _I),
     'ofb_warp_t_win_bwd': ([_P, _L, _F, _P, _L, _P, _F, _P, _P, _L, _I, _I, _I, _I, _P, _P], _I),
     'ofb_splat_s_workspace': ([_I, _I, _I, _I, _I], _L),

@@ -578,6 +578,84 @@ class _WarpTWin(torch.autograd.Function):
         return gflow, gsrc, None, None, None, None, None, None
 
 
+_lib.define("warp_t_inset_fwd(Tensor flow, Tensor src, Tensor? src_mask, Tensor? flow_mask, float thresh, "
+            "bool want_valid, int[] fwin) -> (Tensor, Tensor)")
+_lib.define("warp_t_inset_bwd(Tensor flow, Tensor src, Tensor gout, bool need_gflow, bool need_gsrc, int[] fwin) -> "
+            "(Tensor, Tensor)")
+
+
+def _fwin_arr(fwin):
+    if len(fwin) != 4:
+        raise ValueError("fwin needs 4 integers (y0, x0, flow_h, flow_w)")
+    return (ctypes.c_int * 4)(*[int(v) for v in fwin])
+
+
+def _warp_t_inset_fwd(flow, src, src_mask, flow_mask, thresh, want_valid, fwin):
+    require_cuda(flow, "flow")
+    flow, src = _f32c(flow), _f32c(src)
+    src_mask, flow_mask = _maskc(src_mask), _maskc(flow_mask)
+    _, _, fh, fw = flow.shape
+    _, c, h, w = src.shape
+    n = _batch(flow.shape[0], src, src_mask, flow_mask)
+    dev = flow.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=dev)
+        valid = torch.empty((n, h, w) if want_valid else (0,), dtype=torch.bool, device=dev)
+        _call("ofb_warp_t_inset_fwd", _p(flow), _bs(flow, n, 2 * fh * fw), _p(src), _bs(src, n, c * h * w),
+              _p(src_mask), _bs(src_mask, n, h * w), _p(flow_mask), _bs(flow_mask, n, fh * fw), thresh,
+              _p(out), _p(valid) if want_valid else None, n, c, h, w, _fwin_arr(fwin), _stream())
+    return out, valid
+
+
+def _warp_t_inset_bwd(flow, src, gout, need_gflow, need_gsrc, fwin):
+    require_cuda(flow, "flow")
+    flow, src, gout = _f32c(flow), _f32c(src), _f32c(gout)
+    n, c, h, w = gout.shape
+    _, _, fh, fw = flow.shape
+    dev = flow.device
+    with torch.cuda.device(dev):
+        gflow = torch.empty((n, 2, fh, fw) if need_gflow else (0,), dtype=torch.float32, device=dev)
+        gsrc = torch.empty(tuple(src.shape) if need_gsrc else (0,), dtype=torch.float32, device=dev)
+        _call("ofb_warp_t_inset_bwd", _p(flow), _bs(flow, n, 2 * fh * fw), _p(src), _bs(src, n, c * h * w), _p(gout),
+              _p(gflow) if need_gflow else None, _p(gsrc) if need_gsrc else None, _bs(src, n, c * h * w),
+              n, c, h, w, _fwin_arr(fwin), _stream())
+    return gflow, gsrc
+
+
+_lib.impl("warp_t_inset_fwd", _warp_t_inset_fwd, "CUDA")
+_lib.impl("warp_t_inset_bwd", _warp_t_inset_bwd, "CUDA")
+
+
+class _WarpTInset(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow, src, src_mask, flow_mask, thresh, want_valid, fwin):
+        out, valid = _ops.warp_t_inset_fwd(flow, src, src_mask, flow_mask, thresh, want_valid, fwin)
+        ctx.save_for_backward(flow, src)
+        ctx.fwin = list(fwin)
+        ctx.mark_non_differentiable(valid)
+        ctx.set_materialize_grads(False)
+        return out, valid
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, _gvalid):
+        flow, src = ctx.saved_tensors
+        need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gflow = gsrc = None
+        if gout is not None and (need_gflow or need_gsrc):
+            gf, gs = _ops.warp_t_inset_bwd(flow, src, gout, need_gflow, need_gsrc, ctx.fwin)
+            gflow = _reduce_to(gf, flow) if need_gflow else None
+            gsrc = gs if need_gsrc else None
+        return gflow, gsrc, None, None, None, None, None
+
+
+def warp_t_inset(flow, src, top_left, src_mask=None, flow_mask=None, thresh=0.99999, want_valid=False):
+    """W of the whole frame of `src` by a flow that covers only the window at `top_left` = (y0, x0) and is zero
+    elsewhere; valid is false outside the window (include/oflib_b200.h: ofb_warp_t_inset_fwd)."""
+    fwin = [int(top_left[0]), int(top_left[1]), int(flow.shape[-2]), int(flow.shape[-1])]
+    return _WarpTInset.apply(flow, src, src_mask, flow_mask, float(thresh), bool(want_valid), fwin)
+
+
 def warp_t_win(flow, src, window, src_mask=None, flow_mask=None, sign=1.0, thresh=0.99999, want_valid=False):
     """Windowed W (see include/oflib_b200.h: ofb_warp_t_win_fwd).  window = (y0, x0, gh, gw, sy0, sx0, sh, sw)."""
     return _WarpTWin.apply(flow, src, src_mask, flow_mask, float(sign), float(thresh), bool(want_valid),

@@ -6,4 +6,4 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 "$NVCC" -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
     -Xcompiler -fPIC -shared ${OFB_NVCC_EXTRA} \
-    -o liboflib_b200.so api.cu stats.cu warp_t.cu warp_t_adj.cu warp_t_tile.cu splat_s.cu track.cu ingest.cu rowband.cu
+    -o liboflib_b200.so api.cu stats.cu warp_t.cu warp_t_adj.cu warp_t_tile.cu warp_t_inset.cu splat_s.cu track.cu ingest.cu rowband.cu

@@ -476,6 +476,11 @@ class Flow(object):
             # (flow_class.py:917-918) is materialised.
             return self._finish_apply(*self._warp_window(t, mask, need_valid, padding), target if return_flow else None,
                                       return_dtype, return_2d, return_3d, return_valid_area)
+        if padding is not None and not cut and self._ref == 't':
+            # Fused padding without the cut (flow_class.py:905-934): the whole target frame is warped by a flow that is
+            # zero outside its window; the valid area is false out there.  No padded flow / mask is materialised.
+            return self._finish_apply(*self._warp_inset(t, mask, need_valid, padding), target if return_flow else None,
+                                      return_dtype, return_2d, return_3d, return_valid_area)
         if padding is not None and cut and self._ref == 's' and consider_mask and t.shape[1] <= 6:
             # Fused padding for 's' flows.  The reference pads the flow with replicated vectors and
             # a False mask (flow_class.py:905-914), splats the whole padded frame and cuts the window back out
@@ -538,6 +543,24 @@ class Flow(object):
             return out, valid
         out, valid = _ops.warp_t_win(self._vecs, t, [top, left, th, tw, 0, 0, th, tw], mask if need_valid else None,
                                      self._mask if need_valid else None, want_valid=need_valid)
+        return out, (valid if need_valid else None)
+
+    def _warp_inset(self, t: torch.Tensor, mask: Optional[torch.Tensor], need_valid: bool, padding: list):
+        """'t' warp of the WHOLE target frame by this flow sitting at (top, left) of it, zero elsewhere
+        (padding without the cut), with apply_flow's zero-flow early-out."""
+        top, left = padding[0], padding[2]
+        fh, fw = self.shape[1], self.shape[2]
+        n = max(t.shape[0], self.shape[0])
+        if self._all_zero(thresholded=True, masked=False):           # utils.py:497-498: the target comes back unchanged
+            out = t if t.shape[0] == n else t.expand(n, -1, -1, -1)
+            valid = None
+            if need_valid:                                            # flow_class.py:924-932
+                valid = torch.zeros((n,) + tuple(t.shape[2:]), dtype=torch.bool, device=self._device)
+                inner = mask[..., top:top + fh, left:left + fw] if mask is not None else True
+                valid[:, top:top + fh, left:left + fw] = self._mask & inner
+            return out, valid
+        out, valid = _ops.warp_t_inset(self._vecs, t, (top, left), mask if need_valid else None,
+                                       self._mask if need_valid else None, want_valid=need_valid)
         return out, (valid if need_valid else None)
 
     def _splat_window(self, t: torch.Tensor, mask: Optional[torch.Tensor], need_valid: bool, padding: list):

@@ -183,6 +183,47 @@ def test_fused_padding_is_bit_identical_to_the_padded_path():
     assert torch.equal(vg.cpu(), bigm[:, pad[0]:pad[0] + h, pad[2]:pad[2] + w] & fmask)
 
 
+def test_fused_padding_without_cut_is_bit_identical_to_the_padded_path():
+    """Flow.apply(padding=..., cut=False) for 't' flows (reference flow_class.py:905-934) runs the inset-flow kernel: the
+    whole target frame warped by a flow that is zero outside its window, valid area false out there; no F.pad.  Checked
+    against the oracle (which pads like the reference), gradients included, and for a Flow target and a zero flow."""
+    o = orc()
+    n, c, h, w = 2, 3, 40, 52
+    pad = [5, 3, 7, 2]
+    flow = smooth_flow(n, h, w, 3.0, 990)
+    fmask = holed_mask(n, h, w, 991)
+    big = torch.rand(n, c, h + pad[0] + pad[1], w + pad[2] + pad[3], generator=gen(992))
+    bigm = torch.rand(n, h + pad[0] + pad[1], w + pad[2] + pad[3], generator=gen(993)) > 0.1
+    gout = torch.randn(big.shape, generator=gen(994))
+    fo, bo = flow.clone().requires_grad_(), big.clone().requires_grad_()
+    oo, vo = o.OFlow(fo, 't', fmask).apply(bo, bigm, return_valid_area=True, padding=pad, cut=False)
+    oo.backward(gout)
+    fg, bg = flow.cuda().requires_grad_(), big.cuda().requires_grad_()
+    from oflibpytorch_b200 import _native
+    launches = _native.launch_count()
+    og, vg = of().Flow(fg, 't', fmask.cuda()).apply(bg, bigm.cuda(), return_valid_area=True, padding=pad, cut=False)
+    assert og.shape == big.shape and vg.shape == bigm.shape
+    assert torch.equal(og.detach().cpu(), oo.detach()) and torch.equal(vg.cpu(), vo)
+    og.backward(gout.cuda())
+    assert_grad_close(fg.grad, fo.grad, 'gflow (window-sized)')
+    assert_grad_close(bg.grad, bo.grad, 'gradient of the whole target frame')
+    assert not bool(vg[:, :pad[0]].any()) and not bool(vg[:, :, :pad[2]].any())
+    # single batch item flow against a batch of targets, no valid area, 3-d target
+    o1 = o.OFlow(flow[:1], 't', fmask[:1]).apply(big, padding=pad, cut=False)
+    g1 = of().Flow(flow[:1].cuda(), 't', fmask[:1].cuda()).apply(big.cuda(), padding=pad, cut=False)
+    assert torch.equal(g1.cpu(), o1)
+    # Flow target
+    fb = smooth_flow(n, h + pad[0] + pad[1], w + pad[2] + pad[3], 2.0, 995)
+    ro = o.OFlow(flow, 't', fmask).apply(o.OFlow(fb, 't', bigm), padding=pad, cut=False)
+    rg = of().Flow(flow.cuda(), 't', fmask.cuda()).apply(of().Flow(fb.cuda(), 't', bigm.cuda()), padding=pad, cut=False)
+    assert torch.equal(rg.vecs.cpu(), ro.vecs) and torch.equal(rg.mask.cpu(), ro.mask)
+    # zero flow: the target comes back, valid only inside the window
+    z = of().Flow(torch.zeros(n, 2, h, w, device='cuda'), 't', fmask.cuda())
+    og, vg = z.apply(big.cuda(), bigm.cuda(), return_valid_area=True, padding=pad, cut=False)
+    zo, zv = o.OFlow(torch.zeros(n, 2, h, w), 't', fmask).apply(big, bigm, return_valid_area=True, padding=pad, cut=False)
+    assert torch.equal(og.cpu(), zo) and torch.equal(vg.cpu(), zv)
+
+
 def test_padded_s_apply_with_cut_equals_the_reference_padded_path():
     """Flow.apply(padding=..., cut=True) for 's' flows: the reference pads flow (replicate) and mask (False), splats the
     whole padded frame and cuts.  With consider_mask the padded sources are ignored, so this package splats only the
