@@ -396,7 +396,7 @@ class Flow(object):
                     valid = valid.expand(n, -1, -1)
                 if out.shape[0] != n:
                     out = out.expand(n, -1, -1, -1)
-                if self._ref == 't' and flow_mask_and:
+                if (self._ref == 't' and flow_mask_and) or (self._ref == 's' and consider_mask and flow_mask_and):
                     valid = valid & self._mask
             return out, valid
         if self._ref == 't':
@@ -406,6 +406,7 @@ class Flow(object):
         else:
             if consider_mask and payload_mask is self._mask:
                 payload_mask = None      # every source that is used has mask channel 1: the "bad weight" plane is zero
+            # (with consider_mask a None payload mask means "the flow mask itself": same shortcut)
             out, _d, _w, valid = _ops.splat_flow(self._vecs, payload, payload_mask,
                                                  self._mask if consider_mask else None, sign=sign,
                                                  occlude_zero=True, valid_mode=VALID_GT if need_valid else VALID_NONE)
@@ -507,6 +508,11 @@ class Flow(object):
                 pm = torch.zeros((n,) + tuple(base.shape[1:]), dtype=torch.bool, device=self._device)
                 pm[:, top:top + fh, left:left + fw] = base[:, top:top + fh, left:left + fw] & self._mask
                 payload_mask = pm
+            elif consider_mask:
+                # The reference warps (target mask & flow mask) (flow_class.py:895).  Sources outside the flow mask carry
+                # no weight when the mask is considered, so the AND is implied and never materialised; the zero-flow
+                # early-out of _warp, which returns the mask channel itself, applies it.
+                payload_mask = mask
             else:
                 payload_mask = self._mask if mask is None else (mask & self._mask)
 
