@@ -102,6 +102,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -115,16 +122,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        # nvidia-smi is started BEFORE the warm-up (its first sample takes ~0.1 s, as long as the whole timed region);
+        # only the samples that arrived inside the timed region count (a sample describes the 20 ms before it arrives)
+        rows = self.rows
+        if self.t0 is not None and self.t1 is not None:
+            inside = [r for r in rows if self.t0 <= r[0] <= self.t1 + 0.03]
+            rows = inside if inside else rows[-3:]
+        for _t, r in rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 6:
                 continue
@@ -362,7 +375,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=4, help='batch of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-chunk', type=int, default=8, help='batch items per pipelined chunk of the e2e path')
+    ap.add_argument('--e2e-chunk', type=int, default=4, help='batch items per pipelined chunk of the e2e path')
     ap.add_argument('--validation', default='deferred', choices=['eager', 'deferred'],
                     help="flow validation mode of the package (eager = one host read per user flow, the reference's contract)")
     ap.add_argument('--no-workloads', action='store_true', help='skip combine_flows and configs 3, 4, 5')
@@ -417,24 +430,26 @@ def main():
 
     n = args.batch
     px = n * H * W
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()              # long before the timed region: nvidia-smi needs ~0.1 s for its first sample
     flow, img, mask, tmask, gout = make_inputs(n, dev, seed0=2 + 10 * rank, sigma=args.sigma)
 
     # ---------------------------------------------------------------- device-resident timing
     for _ in range(args.warmup):
         gpu_step(of, flow, img, mask, tmask, gout)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     _native.launch_count_reset()
     _ops.PROFILE = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         gpu_step(of, flow, img, mask, tmask, gout)
     e1.record()
     barrier()
+    sampler.mark_end()
     of.check_deferred()
     clocks = sampler.stop() if rank == 0 else None
     launches = _native.launch_count()

@@ -19,7 +19,7 @@ class HostWarpPipeline:
     upstream gradient) on pinned host buffers.  Results land in caller-provided (or internally allocated) pinned host
     tensors.  One instance per device; reuse it across steps so the device buffers are allocated once."""
 
-    def __init__(self, device: torch.device, chunk: int = 8):
+    def __init__(self, device: torch.device, chunk: int = 4):
         self.device = torch.device(device)
         self.chunk = int(chunk)
         self.s_h2d = torch.cuda.Stream(self.device)
