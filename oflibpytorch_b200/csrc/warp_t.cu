@@ -823,7 +823,7 @@ static bool window_ok(const Window &w, int H, int W)
 {
     return H >= 1 && W >= 1 && w.gh >= 2 && w.gw >= 2 && w.sh >= 1 && w.sw >= 1 && w.y0 >= 0 && w.x0 >= 0 &&
            w.y0 + H <= w.gh && w.x0 + W <= w.gw && w.sy0 >= 0 && w.sx0 >= 0 && w.sy0 + w.sh <= w.gh &&
-           w.sx0 + w.sw <= w.gw && (int64_t)w.sh * w.sw <= 0x3fffffff && (int64_t)H * W <= 0x3fffffff;
+           w.sx0 + w.sw <= w.gw && (int64_t)w.sh * w.sw <= 0x1fffffff && (int64_t)H * W <= 0x1fffffff;   // 4 planes of 32-bit offsets
 }
 
 static bool window_is_identity(const Window &w, int H, int W)

@@ -116,7 +116,7 @@ static int inset_check(int N, int C, int H, int W, const int *fwin)
     if (H < 2 || W < 2) return OFB_ESHAPE;
     if (fwin[0] < 0 || fwin[1] < 0 || fwin[2] < 1 || fwin[3] < 1 || fwin[0] + fwin[2] > H || fwin[1] + fwin[3] > W)
         return OFB_EINVAL;
-    if ((int64_t)H * W > 0x3fffffff) return OFB_EINVAL;
+    if ((int64_t)H * W > 0x1fffffff) return OFB_EINVAL;
     return 0;
 }
 

@@ -38,6 +38,9 @@ __global__ void k_smem(float* out, int iters, int mode) {
         else if (mode == 4) { r = r * 1664525u + 1013904223u; atomicAdd(reinterpret_cast<int*>(&acc[(r >> 8) & 8191]), 1); }
         else if (mode == 5) { atomicAdd(reinterpret_cast<unsigned long long*>(&acc[((warp * 997 + it * 37 + lane) * 2) & 8190]), 1ull); }
         else if (mode == 6) { atomicAdd(reinterpret_cast<int*>(&acc[(warp * 997 + it * 37 + lane - (lane >> 3)) & 8191]), 1); }   // 3 duplicate pairs per warp-op
+        else if (mode >= 8) { int a = (warp * 997 + it * 37 + lane) & 8191; const int act = mode == 8 ? 16 : (mode == 9 ? 8 : 32);
+               if (lane < act) { atomicAdd(reinterpret_cast<int*>(&acc[a]), 2); atomicAdd(reinterpret_cast<int*>(&acc[(a + 1) & 8191]), 3);
+               atomicAdd(reinterpret_cast<int*>(&acc[(a + 96) & 8191]), 4); atomicAdd(reinterpret_cast<int*>(&acc[(a + 97) & 8191]), 5); } }
         else { int a = (warp * 997 + it * 37 + lane) & 8191; atomicAdd(reinterpret_cast<int*>(&acc[a]), 1); atomicAdd(reinterpret_cast<int*>(&acc[(a + 1) & 8191]), 2);
                atomicAdd(reinterpret_cast<int*>(&acc[(a + 96) & 8191]), 3); atomicAdd(reinterpret_cast<int*>(&acc[(a + 97) & 8191]), 4); }
     }
@@ -69,13 +72,13 @@ int main() {
         cudaFree(buf);
     }
     float* o; cudaMalloc(&o, 4);
-    for (int mode = 0; mode < 8; ++mode) {
+    for (int mode = 0; mode < 11; ++mode) {
         int grid = 148 * 4, block = 256, iters = 4096;
         k_smem<<<grid, block>>>(o, 16, mode); CK(cudaDeviceSynchronize());
         cudaEventRecord(e0); k_smem<<<grid, block>>>(o, iters, mode); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
         cudaEventElapsedTime(&ms, e0, e1);
         double ops = (double)grid * block * iters;
-        const char* nm[] = {"smem atomicAdd f32 consecutive", "smem atomicAdd f32 random", "smem plain RMW + syncwarp", "smem atomicAdd i32 consecutive", "smem atomicAdd i32 random", "smem atomicAdd u64 consecutive", "smem atomicAdd i32 consecutive, 3 duplicate pairs", "smem atomicAdd i32 4 taps per iteration (ops counted per iteration)"};
+        const char* nm[] = {"smem atomicAdd f32 consecutive", "smem atomicAdd f32 random", "smem plain RMW + syncwarp", "smem atomicAdd i32 consecutive", "smem atomicAdd i32 random", "smem atomicAdd u64 consecutive", "smem atomicAdd i32 consecutive, 3 duplicate pairs", "smem atomicAdd i32 4 taps per iteration (ops counted per iteration)", "4 taps, 16 of 32 lanes active", "4 taps, 8 of 32 lanes active", "4 taps, 32 lanes (ATOMS.ADD form)"};
         printf("%s: %.1f G lane-ops/s  (%.2f clk per warp-op per SM at 1.965 GHz)\n", nm[mode], ops / ms / 1e6,
                1.965e9 / (ops / 32 / 148 / (ms * 1e-3)));
     }
