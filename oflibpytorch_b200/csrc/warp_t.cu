@@ -11,8 +11,9 @@
 //   staged  (opt-in, OFB_TMA=1): a CTA streams its tile's flow, reduces the bounding box of the sample positions and
 //           has one thread issue TMA box copies (cp.async.bulk.tensor.3d) of that source region into shared memory,
 //           zero-filled outside the image by the TMA unit; taps are then LDS [reg + imm].  Parity-green but slower
-//           (0.42 of the HBM peak against 0.62): the box over-fetches and the load -> TMA -> compute phases of a CTA do
-//           not overlap.
+//           (0.52 of the HBM peak against 0.63 on the benchmark's flow field with 32 x 32 tiles and 64 x 48 boxes, 5 CTAs
+//           per SM; 0.43 with the first geometry, 64 x 32 tiles / 80 x 48 boxes / 3 CTAs): the box over-fetches 3x from
+//           L2 and the load -> TMA -> compute phases of a CTA do not overlap.
 // All three are bounded by the L1 data pipe, not by HBM: a tap row of 32 lanes is an unaligned 128-byte span that
 // drifts over several image rows (7.3 sectors and 2.3 wavefronts per load on the benchmark's flow field), and
 // l1tex__data_pipe_lsu_wavefronts sits at 70 % of its peak whatever the instruction count (the lean kernel issues
@@ -423,10 +424,26 @@ __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(con
 // ------------------------------------------------------------------------------------------------
 // staged forward
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileW = 64, kTileH = 32, kRows = 8;        // 8 warps: 2 across x, 4 across y, 8 rows per thread
-constexpr int kBoxW = 80, kBoxH = 48;                     // staged source region (floats): tile + 16 of slack
+#ifndef OFB_ST_TW
+#define OFB_ST_TW 32
+#endif
+#ifndef OFB_ST_ROWS
+#define OFB_ST_ROWS 4
+#endif
+#ifndef OFB_ST_BOXW
+#define OFB_ST_BOXW 64
+#endif
+#ifndef OFB_ST_BOXH
+#define OFB_ST_BOXH 48
+#endif
+#ifndef OFB_ST_MINB
+#define OFB_ST_MINB 5
+#endif
+constexpr int kTileW = OFB_ST_TW, kStWX = kTileW / 32, kRows = OFB_ST_ROWS;   // 8 warps: kStWX across x, 8 / kStWX across y
+constexpr int kTileH = (8 / kStWX) * kRows;
+constexpr int kBoxW = OFB_ST_BOXW, kBoxH = OFB_ST_BOXH;   // staged source region (floats): tile + slack
 constexpr int kPlane = kBoxW * kBoxH;                     // elements per staged channel
-constexpr int kMBoxW = 96;                                // byte-mask box is wider: its origin is 16-pixel aligned
+constexpr int kMBoxW = kBoxW + 16;                        // byte-mask box is wider: its origin is 16-pixel aligned
 constexpr int kMaxCN = 4;                                 // payload channels staged per launch
 // TMA needs the box origin 16-byte aligned along x: multiples of 4 floats / 16 mask bytes (measured: anything else
 // raises an illegal-instruction fault).  Rounding the origin down costs at most 3 (15) columns of the box.
@@ -445,7 +462,7 @@ constexpr int staged_smem_bytes(int cn, int vmode)
 // CN    payload channels handled by this launch (1..4), planes [c_off, c_off + CN) of C_total
 // VMODE 0: no validity output; 1: validity with an all-true payload mask; 2: validity with a staged payload mask
 template <int CN, int VMODE>
-__global__ void __launch_bounds__(256, 3) warp_t_fwd_staged_kernel(const WarpFwdParams p,
+__global__ void __launch_bounds__(256, OFB_ST_MINB) warp_t_fwd_staged_kernel(const WarpFwdParams p,
                                                                    const __grid_constant__ CUtensorMap src_map,
                                                                    const __grid_constant__ CUtensorMap mask_map,
                                                                    const int c_off, const CoordCtx cc)
@@ -456,8 +473,8 @@ __global__ void __launch_bounds__(256, 3) warp_t_fwd_staged_kernel(const WarpFwd
     StageCtl &ctl = *reinterpret_cast<StageCtl *>(smem + kPlane * 4 * CN + (VMODE == 2 ? kMBoxW * kBoxH : 0));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * kTileW + (warp & 1) * 32 + lane;
-    const int y0 = blockIdx.y * kTileH + (warp >> 1) * kRows;
+    const int x = blockIdx.x * kTileW + (warp % kStWX) * 32 + lane;
+    const int y0 = blockIdx.y * kTileH + (warp / kStWX) * kRows;
     const int n = blockIdx.z;
     const int HW = p.H * p.W;
     const int xc = min(x, p.W - 1);                       // clamped copies for loads; stores are predicated
