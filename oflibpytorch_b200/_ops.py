@@ -36,6 +36,35 @@ _lib.define("splat_s_bwd(Tensor cx, Tensor cy, bool relative, float sign, Tensor
             "bool need_gcoord, bool need_gdata, int[] window) -> (Tensor, Tensor)")
 
 
+# The two hot W ops are also registered from C++ (csrc/torch_binding.cpp, TORCH_LIBRARY oflib_b200n): same C-ABI calls,
+# outputs allocated by ATen, no ctypes on the way.  The autograd wrapper below dispatches to them when the shim is built
+# (csrc/build.sh builds it); OFB_NO_TORCH_BINDING=1 keeps the Python-registered twins (tuning / comparison).
+def _load_native_ops():
+    import os
+    path = os.path.join(os.path.dirname(_native.LIB_PATH), 'liboflib_b200_torch.so')
+    if os.environ.get('OFB_NO_TORCH_BINDING') or os.environ.get('OFB_LIB_OVERRIDE') or not os.path.exists(path):
+        return None
+    _native.lib()                      # liboflib_b200.so first: a missing kernel library must fail loudly, by name
+    torch.ops.load_library(path)
+    return torch.ops.oflib_b200n
+
+
+_NATIVE = _load_native_ops()
+
+
+def _native_op(name: str, abi_name: str, *args):
+    """Call a C++-registered op, bracketed by CUDA events like _call when bench.py profiles."""
+    fn = getattr(_NATIVE, name)
+    if PROFILE is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = fn(*args)
+    e1.record()
+    PROFILE.append((abi_name, e0, e1))
+    return res
+
+
 # Optional per-call device timing (bench.py): when PROFILE is a list, every C-ABI call is bracketed by CUDA events
 # recorded on the launching stream and (name, start, end) is appended.  None (default) = no events.
 PROFILE = None
@@ -362,8 +391,13 @@ class _WarpT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, flow, src, src_mask, flow_mask, sign, add_flow, thresh, want_valid, sel, want_flags):
         want_dtaps = SAVE_DERIVATIVES and ctx.needs_input_grad[0]
-        out, valid, out_flags, dtaps = _ops.warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh, want_valid,
-                                                       sel, want_flags, want_dtaps)
+        if _NATIVE is not None:
+            require_cuda(flow, "flow")
+            out, valid, out_flags, dtaps = _native_op("warp_t_fwd", "ofb_warp_t_fwd", flow, sign, src, src_mask,
+                                                      flow_mask, add_flow, thresh, want_valid, sel, want_flags, want_dtaps)
+        else:
+            out, valid, out_flags, dtaps = _ops.warp_t_fwd(flow, sign, src, src_mask, flow_mask, add_flow, thresh,
+                                                           want_valid, sel, want_flags, want_dtaps)
         ctx.save_for_backward(flow, src, sel, dtaps if dtaps.numel() else None)
         ctx.sign, ctx.add_flow = sign, add_flow
         ctx.mark_non_differentiable(valid, out_flags)
@@ -377,7 +411,11 @@ class _WarpT(torch.autograd.Function):
         need_gflow, need_gsrc = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gflow = gsrc = None
         if gout is not None and (need_gflow or need_gsrc):
-            gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc, sel, dtaps)
+            if _NATIVE is not None:
+                gf, gs = _native_op("warp_t_bwd", "ofb_warp_t_bwd", flow, ctx.sign, src, gout, ctx.add_flow, need_gflow,
+                                    need_gsrc, sel, dtaps)
+            else:
+                gf, gs = _ops.warp_t_bwd(flow, ctx.sign, src, gout, ctx.add_flow, need_gflow, need_gsrc, sel, dtaps)
             if need_gflow:
                 gflow = _reduce_to(gf, flow)
             if need_gsrc:

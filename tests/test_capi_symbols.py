@@ -74,3 +74,15 @@ def test_header_is_valid_c99_and_links_from_plain_c(tmp_path):
                     '-L', libdir, '-l:liboflib_b200.so', '-Wl,-rpath,' + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert out.startswith('1 ') and 'invalid' in out
+
+
+def test_torch_library_shim_registers_the_hot_ops():
+    """csrc/torch_binding.cpp: the two hot W ops registered from C++ (TORCH_LIBRARY oflib_b200n), CUDA key only."""
+    import pytest
+    import torch
+    from oflibpytorch_b200 import _ops
+    assert _ops._NATIVE is not None, 'liboflib_b200_torch.so missing: run __graft_entry__.build()'
+    for name in ('warp_t_fwd', 'warp_t_bwd'):
+        assert hasattr(torch.ops.oflib_b200n, name)
+    with pytest.raises(RuntimeError):        # no CPU kernel, no fallback: the package's own message comes first
+        _ops.warp_t(torch.zeros(1, 2, 4, 4), torch.zeros(1, 1, 4, 4))
