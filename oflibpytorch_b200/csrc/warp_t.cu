@@ -319,7 +319,8 @@ constexpr int kLeanRows = OFB_LEAN_ROWS;
 //   * WANT_D: the kernel also writes d out[c] / d ix and d out[c] / d iy (2C planes).  The adjoint's flow gradient is
 //     then a stream (sum_c gout[c] * d[c]) instead of a second gather of the 4C payload taps, which is what bounds
 //     both kernels (L1 wavefronts of unaligned tap rows): 24 B/pixel more traffic for C = 3, about 30 % less adjoint.
-template <int CN, bool WANT_VALID, bool STATS, bool WANT_D>
+//   * WIN: windowed frame (struct Window: padded apply with cut, row bands); the taps live in stored-region coordinates.
+template <int CN, bool WANT_VALID, bool STATS, bool WANT_D, bool WIN = false>
 __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(const WarpFwdParams p, const CoordCtx cc)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -333,6 +334,8 @@ __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(con
     const int rows = (STATS && !inside) ? 0 : min(kLeanRows, p.H - y0);
     // per-item bases: functions of blockIdx.z only
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
+    const Window wn = WIN ? p.win : Window{0, 0, p.H, W, 0, 0, p.H, W};
+    const int SW = wn.sw, SH = wn.sh, HWs = SH * SW;      // stored source region (the field itself without a window)
     const float *src = p.src + (int64_t)n * p.src_bs;
     float *out = p.out + (int64_t)n * CN * HW;
     const uint8_t *smask = p.src_mask ? p.src_mask + (int64_t)n * p.src_mask_bs : nullptr;
@@ -351,8 +354,7 @@ __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(con
             fy[r] = __ldg(fl + (HW + q));
         }
     }
-    const float xf = (float)x;
-    const Window wn{0, 0, p.H, W, 0, 0, p.H, W};
+    const float xf = (float)(x + wn.x0);
     OutStats os{0u, 0u};
 #pragma unroll
     for (int r = 0; r < kLeanRows; ++r) {
@@ -360,20 +362,21 @@ __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(con
         const int pix = (y0 + r) * W + x;
         float ix, iy;
         ix = round_trip_unchecked(__fmaf_rn(-cc.sign, fx[r], xf), cc.dw);
-        iy = round_trip_unchecked(__fmaf_rn(-cc.sign, fy[r], (float)(y0 + r)), cc.dh);
-        const int xi = __float2int_rd(ix), yi = __float2int_rd(iy);
-        const bool all_in = (unsigned)xi < (unsigned)(W - 1) && (unsigned)yi < (unsigned)(p.H - 1);
+        iy = round_trip_unchecked(__fmaf_rn(-cc.sign, fy[r], (float)(y0 + r + wn.y0)), cc.dh);
+        const int xi = (int)((unsigned)__float2int_rd(ix) - (unsigned)wn.sx0);       // stored-region coordinates
+        const int yi = (int)((unsigned)__float2int_rd(iy) - (unsigned)wn.sy0);
+        const bool all_in = (unsigned)xi < (unsigned)(SW - 1) && (unsigned)yi < (unsigned)(SH - 1);
         if (__all_sync(live, all_in)) {   // lanes right of the field never get here
             const float x0 = floorf(ix), y0f = floorf(iy);
             const float ex = __fsub_rn(__fadd_rn(x0, 1.0f), ix), wx = __fsub_rn(ix, x0);
             const float sy = __fsub_rn(__fadd_rn(y0f, 1.0f), iy), ny = __fsub_rn(iy, y0f);
             const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
-            const int o = yi * W + xi;
+            const int o = yi * SW + xi;
             unsigned okbit = 1u;
             if (WANT_VALID) {
                 float m;
                 if (smask) {
-                    const uint8_t *mn = smask + o, *ms = smask + (o + W);
+                    const uint8_t *mn = smask + o, *ms = smask + (o + SW);
                     const float a = mask_to_float(__ldg(mn)), b = mask_to_float(__ldg(mn + 1));
                     const float c = mask_to_float(__ldg(ms)), d = mask_to_float(__ldg(ms + 1));
                     m = __fmaf_rn(d, wse, __fmaf_rn(c, wsw, __fmaf_rn(b, wne, __fmul_rn(a, wnw))));
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(con
             }
 #pragma unroll
             for (int c = 0; c < CN; ++c) {
-                const float *tn = src + (c * HW + o), *ts = src + (c * HW + o + W);
+                const float *tn = src + (c * HWs + o), *ts = src + (c * HWs + o + SW);
                 const float a = __ldg(tn), b = __ldg(tn + 1), cq = __ldg(ts), d = __ldg(ts + 1);
                 float v = __fmaf_rn(d, wse, __fmaf_rn(cq, wsw, __fmaf_rn(b, wne, __fmul_rn(a, wnw))));
                 if (p.add_flow != 0.0f && c < 2)                                 // flow_class.py:1804,1808
@@ -405,13 +408,13 @@ __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(con
             }
         } else {
             ItemPtrs ip{src, out, smask, fmask, valid};
-            const PixGeom g = pix_geom<false>(ix, iy, wn);
+            const PixGeom g = pix_geom<WIN>(ix, iy, wn);
             warp_pixel_direct<CN, WANT_VALID, false, STATS>(p, wn, ip, g, pix, fx[r], fy[r], 0, CN, &os);
             if (WANT_D) {
 #pragma unroll
                 for (int c = 0; c < CN; ++c) {
                     float a, b, cq, d;
-                    load_taps<false, float>(src + (c * HW + g.o), src + (c * HW + g.o + W), g, a, b, cq, d);
+                    load_taps<false, float>(src + (c * HWs + g.o), src + (c * HWs + g.o + SW), g, a, b, cq, d);
                     dt[(2 * c) * HW + pix] = __fmaf_rn(b - a, g.sy, (d - cq) * g.ny);
                     dt[(2 * c + 1) * HW + pix] = __fmaf_rn(cq - a, g.ex, (d - b) * g.wx);
                 }
@@ -932,11 +935,12 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
         dim3 lgrid = grid;
         // (with out_flags -- the result's flags, combine mode 3 -- the direct kernel is the faster one: the lean kernel
         // spills at 32 registers once it carries the two maxima, measured 1.31 against 1.42 ms at 16 x 4K)
-        const bool lean = (g_fwd_impl == 0 || dtaps) && (!out_flags || dtaps) && win_id && cn >= 1 && kLeanRows == kDirRows &&
-                          W <= 65536 && H <= 65536;
+        const bool lean = (g_fwd_impl == 0 || dtaps) && (!out_flags || dtaps) && (win_id || !dtaps) && cn >= 1 &&
+                          kLeanRows == kDirRows && win.gw <= 65536 && win.gh <= 65536;
         if (dtaps && !lean) return OFB_EINVAL;
         if (lean) {     // the plain warp: lean kernel
 #define OFB_LEAN(CN_) (dtaps ? (wv ? warp_t_fwd_lean_kernel<CN_, true, false, true> : warp_t_fwd_lean_kernel<CN_, false, false, true>) \
+                       : !win_id ? (wv ? warp_t_fwd_lean_kernel<CN_, true, false, false, true> : warp_t_fwd_lean_kernel<CN_, false, false, false, true>) \
                              : (wv ? warp_t_fwd_lean_kernel<CN_, true, false, false> : warp_t_fwd_lean_kernel<CN_, false, false, false>))
             switch (cn) {
                 case 1: k = OFB_LEAN(1); break;
@@ -978,14 +982,14 @@ static int warp_t_bwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
     const CoordCtx cc{{(float)(win.gw - 1), 1.0f / (float)(win.gw - 1)}, {(float)(win.gh - 1), 1.0f / (float)(win.gh - 1)},
                       flow_sign};
     bool done = false;
-    if (gsrc && window_is_identity(win, H, W)) {
+    if (gsrc) {
         const WarpBwdParams rp{flow, flow_bs, flow_sign, src, src_bs, gout, add_flow, gflow, gsrc, gsrc_bs, N, C, H, W, win,
                                nullptr, dtaps, gout_bcast};
         // tile-owned accumulation (warp_t_tile.cu), the default; 1 = outside its domain
         int rs = warp_t_bwd_tile_launch(rp, cc, st);
         if (rs == 0) done = true;
         else if (rs != 1) return rs;
-        if (!done && !sel) {                        // ring adjoint (warp_t_adj.cu), opt-in experiment
+        if (!done && !sel && window_is_identity(win, H, W)) {      // ring adjoint (warp_t_adj.cu), opt-in experiment
             rs = warp_t_bwd_ring_launch(rp, cc, st);
             if (rs != 1) return rs;
         }

@@ -66,7 +66,9 @@ __device__ __forceinline__ void red_add_v4(float *a, float x, float y, float z, 
 }
 
 // GFLOW: 0 no flow gradient, 1 from the payload taps (global gathers), 2 from the derivative planes the forward saved
-template <int CN, int GFLOW>
+// WIN:   the flow / gout / gflow tensors are a window of a larger frame and src / gsrc a stored region of it (struct Window,
+//        warp_t.cuh: padded apply with cut, row bands); everything about the taps then lives in stored-region coordinates
+template <int CN, int GFLOW, bool WIN>
 __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
                                                                  const int accumulate_gflow, const int vec_ok)
 {
@@ -77,15 +79,18 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
     const int x = blockIdx.x * kTT + lane;
     const int y0 = blockIdx.y * kTT + warp * kTRows;
     const int n = blockIdx.z;
-    const int W = p.W, H = p.H, HW = H * W;
+    const int W = p.W, H = p.H, HW = H * W;                                     // flow / output window
+    const int SW = WIN ? p.win.sw : W, SH = WIN ? p.win.sh : H, HWs = SH * SW;  // stored source region
+    const int X0 = WIN ? p.win.x0 : 0, Y0 = WIN ? p.win.y0 : 0;                 // window origin in the global frame
+    const int SX0 = WIN ? p.win.sx0 : 0, SY0 = WIN ? p.win.sy0 : 0;             // stored region origin
     const bool xin = x < W;
     const int xc = min(x, W - 1);
 
     const float *fl = p.flow + (int64_t)n * p.flow_bs;
-    const float *src = GFLOW == 1 ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HW : nullptr;
+    const float *src = GFLOW == 1 ? p.src + (int64_t)n * p.src_bs + (int64_t)c_off * HWs : nullptr;
     const float *dt = GFLOW == 2 ? p.dtaps + ((int64_t)n * p.C + c_off) * 2 * HW : nullptr;
     const float *go = p.gout_bcast ? p.gout : p.gout + ((int64_t)n * p.C + c_off) * HW;
-    float *gsrc = p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HW;
+    float *gsrc = p.gsrc + (int64_t)n * p.gsrc_bs + (int64_t)c_off * HWs;
     float *gf = GFLOW ? p.gflow + (int64_t)n * 2 * HW : nullptr;
     asm volatile("" : "+l"(src), "+l"(dt), "+l"(go), "+l"(gsrc), "+l"(gf));
 
@@ -112,20 +117,22 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
 #pragma unroll
             for (int c = 0; c < CN; ++c) gv[r][c] = OFB_TILE_LD(go + (p.gout_bcast ? 0 : c * HW + q));
         }
-        const float xf = (float)x;
+        const float xf = (float)(x + X0);
         int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
         unsigned amax = 0u;
 #pragma unroll
         for (int r = 0; r < kTRows; ++r) {
             const bool act = xin && (y0 + r < H);
             ix[r] = round_trip_unchecked(__fmaf_rn(-cc.sign, fx[r], xf), cc.dw);
-            iy[r] = round_trip_unchecked(__fmaf_rn(-cc.sign, fy[r], (float)(y0 + r)), cc.dh);
-            const int xi = __float2int_rd(ix[r]), yi = __float2int_rd(iy[r]);
-            // pixels with at least one tap inside the image stretch the footprint, by their in-image taps only
-            const bool any = act && xi >= -1 && xi <= W - 1 && yi >= -1 && yi <= H - 1;
+            iy[r] = round_trip_unchecked(__fmaf_rn(-cc.sign, fy[r], (float)(y0 + r + Y0)), cc.dh);
+            // tap position in the stored source region (which lies inside the global frame: only its bounds matter)
+            const int xi = (int)((unsigned)__float2int_rd(ix[r]) - (unsigned)SX0);
+            const int yi = (int)((unsigned)__float2int_rd(iy[r]) - (unsigned)SY0);
+            // pixels with at least one tap inside the region stretch the footprint, by those taps only
+            const bool any = act && xi >= -1 && xi <= SW - 1 && yi >= -1 && yi <= SH - 1;
             if (any) {
-                minx = min(minx, max(xi, 0)); maxx = max(maxx, min(xi + 1, W - 1));
-                miny = min(miny, max(yi, 0)); maxy = max(maxy, min(yi + 1, H - 1));
+                minx = min(minx, max(xi, 0)); maxx = max(maxx, min(xi + 1, SW - 1));
+                miny = min(miny, max(yi, 0)); maxy = max(maxy, min(yi + 1, SH - 1));
             }
 #pragma unroll
             for (int c = 0; c < CN; ++c) {
@@ -166,12 +173,13 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
     for (int r = 0; r < kTRows; ++r) {
         if (r >= rows) break;
         const int pix = (y0 + r) * W + xc;
-        const int xi = __float2int_rd(ix[r]), yi = __float2int_rd(iy[r]);
+        const int xi = (int)((unsigned)__float2int_rd(ix[r]) - (unsigned)SX0);      // stored-region coordinates
+        const int yi = (int)((unsigned)__float2int_rd(iy[r]) - (unsigned)SY0);
         const float x0 = floorf(ix[r]), y0f = floorf(iy[r]);
         const float ex = __fsub_rn(__fadd_rn(x0, 1.0f), ix[r]), wx = __fsub_rn(ix[r], x0);
         const float sy = __fsub_rn(__fadd_rn(y0f, 1.0f), iy[r]), ny = __fsub_rn(iy[r], y0f);
-        const int o = yi * W + xi;
-        const bool all_in = (unsigned)xi < (unsigned)(W - 1) && (unsigned)yi < (unsigned)(H - 1);
+        const int o = yi * SW + xi;
+        const bool all_in = (unsigned)xi < (unsigned)(SW - 1) && (unsigned)yi < (unsigned)(SH - 1);
         if (__all_sync(0xffffffffu, all_in && xin)) {
             // ---- every tap of every lane is inside the image: no predicates
             if (GFLOW) {
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
                         dx = __ldg(dt + ((2 * c) * HW + pix));
                         dy = __ldg(dt + ((2 * c + 1) * HW + pix));
                     } else {
-                        const float *tn = src + (c * HW + o), *ts = src + (c * HW + o + W);
+                        const float *tn = src + (c * HWs + o), *ts = src + (c * HWs + o + SW);
                         const float a = __ldg(tn), b = __ldg(tn + 1), cq = __ldg(ts), d = __ldg(ts + 1);
                         // d out / d ix and d out / d iy
                         dx = __fmaf_rn(b - a, sy, (d - cq) * ny);
@@ -217,17 +225,17 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
                 const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
 #pragma unroll
                 for (int c = 0; c < CN; ++c) {
-                    float *t = gsrc + (c * HW + o);
+                    float *t = gsrc + (c * HWs + o);
                     red_add_f32(t, wnw * gv[r][c]);
                     red_add_f32(t + 1, wne * gv[r][c]);
-                    red_add_f32(t + W, wsw * gv[r][c]);
-                    red_add_f32(t + W + 1, wse * gv[r][c]);
+                    red_add_f32(t + SW, wsw * gv[r][c]);
+                    red_add_f32(t + SW + 1, wse * gv[r][c]);
                 }
             }
         } else {
             // ---- border warps: per-tap predicates
-            const bool bx0 = (unsigned)xi < (unsigned)W, bx1 = (unsigned)(xi + 1) < (unsigned)W;
-            const bool by0 = (unsigned)yi < (unsigned)H, by1 = (unsigned)(yi + 1) < (unsigned)H;
+            const bool bx0 = (unsigned)xi < (unsigned)SW, bx1 = (unsigned)(xi + 1) < (unsigned)SW;
+            const bool by0 = (unsigned)yi < (unsigned)SH, by1 = (unsigned)(yi + 1) < (unsigned)SH;
             const bool pnw = xin && bx0 && by0, pne = xin && bx1 && by0, psw = xin && bx0 && by1, pse = xin && bx1 && by1;
             if (GFLOW) {
                 float gix = 0.0f, giy = 0.0f;
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
                         dx = __ldg(dt + ((2 * c) * HW + pix));
                         dy = __ldg(dt + ((2 * c + 1) * HW + pix));
                     } else {
-                        const float *tn = src + (c * HW + o), *ts = src + (c * HW + o + W);
+                        const float *tn = src + (c * HWs + o), *ts = src + (c * HWs + o + SW);
                         float a = 0.0f, b = 0.0f, cq = 0.0f, d = 0.0f;
                         if (pnw) a = __ldg(tn);
                         if (pne) b = __ldg(tn + 1);
@@ -274,11 +282,11 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
                         if (psw) atomicAdd(wp + c * kTPlane + kTWin, __float2int_rn(wsw * gs));
                         if (pse) atomicAdd(wp + c * kTPlane + kTWin + 1, __float2int_rn(wse * gs));
                     } else {
-                        float *t = gsrc + (c * HW + o);
+                        float *t = gsrc + (c * HWs + o);
                         if (pnw) red_add_f32(t, wnw * gv[r][c]);
                         if (pne) red_add_f32(t + 1, wne * gv[r][c]);
-                        if (psw) red_add_f32(t + W, wsw * gv[r][c]);
-                        if (pse) red_add_f32(t + W + 1, wse * gv[r][c]);
+                        if (psw) red_add_f32(t + SW, wsw * gv[r][c]);
+                        if (pse) red_add_f32(t + SW + 1, wse * gv[r][c]);
                     }
                 }
             }
@@ -294,13 +302,13 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
             const int gx = ox + 4 * q;
 #pragma unroll 1
             for (int c = 0; c < CN; ++c) {
-                float *gp = gsrc + (c * HW + gx);
+                float *gp = gsrc + (c * HWs + gx);
                 const int *wc = win + c * kTPlane + 4 * q;
 #pragma unroll 2
                 for (int rr = rr0; rr < ex_h; rr += 16) {
                     const int4 v = *reinterpret_cast<const int4 *>(wc + rr * kTWin);
                     if ((v.x | v.y | v.z | v.w) == 0) continue;
-                    float *g = gp + (oy + rr) * W;
+                    float *g = gp + (oy + rr) * SW;
                     const float a = (float)v.x * inv_scale, b = (float)v.y * inv_scale;
                     const float cq = (float)v.z * inv_scale, d = (float)v.w * inv_scale;
                     if (vec_ok) {
@@ -320,19 +328,20 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
 typedef void (*TileKernel)(const WarpBwdParams, const CoordCtx, const int, const int, const int);
 
 template <int CN>
-static TileKernel tile_kernel_for(int gflow)
+static TileKernel tile_kernel_for(int gflow, bool win)
 {
-    if (gflow == 2) return warp_t_bwd_tile_kernel<CN, 2>;
-    return gflow ? warp_t_bwd_tile_kernel<CN, 1> : warp_t_bwd_tile_kernel<CN, 0>;
+    if (win) return gflow ? warp_t_bwd_tile_kernel<CN, 1, true> : warp_t_bwd_tile_kernel<CN, 0, true>;
+    if (gflow == 2) return warp_t_bwd_tile_kernel<CN, 2, false>;
+    return gflow ? warp_t_bwd_tile_kernel<CN, 1, false> : warp_t_bwd_tile_kernel<CN, 0, false>;
 }
 
-static TileKernel tile_kernel(int cn, int gflow)
+static TileKernel tile_kernel(int cn, int gflow, bool win)
 {
     switch (cn) {
-        case 1: return tile_kernel_for<1>(gflow);
-        case 2: return tile_kernel_for<2>(gflow);
-        case 3: return tile_kernel_for<3>(gflow);
-        default: return tile_kernel_for<4>(gflow);
+        case 1: return tile_kernel_for<1>(gflow, win);
+        case 2: return tile_kernel_for<2>(gflow, win);
+        case 3: return tile_kernel_for<3>(gflow, win);
+        default: return tile_kernel_for<4>(gflow, win);
     }
 }
 
@@ -340,19 +349,23 @@ static TileKernel tile_kernel(int cn, int gflow)
 int warp_t_bwd_tile_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStream_t st)
 {
     if (!(g_bwd_impl < 0 || g_bwd_impl == 7) || !p.gsrc) return 1;
-    if (p.W > 65536 || p.H > 65536 || p.W < 2 || p.H < 2) return 1;      // round_trip_unchecked's domain
-    const int64_t HW = (int64_t)p.H * p.W;
-    const int64_t item_bytes = (int64_t)p.C * HW * 4;
+    const Window &wn = p.win;
+    const bool win = !(wn.y0 == 0 && wn.x0 == 0 && wn.gh == p.H && wn.gw == p.W && wn.sy0 == 0 && wn.sx0 == 0 &&
+                       wn.sh == p.H && wn.sw == p.W);
+    if (wn.gw > 65536 || wn.gh > 65536 || wn.gw < 2 || wn.gh < 2) return 1;      // round_trip_unchecked's domain
+    if (win && (p.dtaps || p.gout_bcast)) return 1;
+    const int64_t HWs = (int64_t)wn.sh * wn.sw;
+    const int64_t item_bytes = (int64_t)p.C * HWs * 4;
     {
         cudaError_t e = cudaMemsetAsync(p.gsrc, 0, (size_t)(p.gsrc_bs == 0 ? item_bytes : item_bytes * p.N), st);
         if (e != cudaSuccess) return (int)e;
     }
-    // 16-byte REDs at the flush: every plane row must start 16-byte aligned
-    const int vec_ok = (p.W % 4 == 0) && aligned16(p.gsrc) && (p.gsrc_bs % 4 == 0);
+    // 16-byte REDs at the flush: every plane row of the stored region must start 16-byte aligned
+    const int vec_ok = (wn.sw % 4 == 0) && aligned16(p.gsrc) && (p.gsrc_bs % 4 == 0);
     const dim3 grid((p.W + kTT - 1) / kTT, (p.H + kTT - 1) / kTT, p.N);
     for (int c0 = 0; c0 < p.C; c0 += 4) {          // channel groups of <= 4; gflow accumulates across groups
         const int cn = (p.C - c0 < 4) ? (p.C - c0) : 4;
-        TileKernel k = tile_kernel(cn, !p.gflow ? 0 : (p.dtaps ? 2 : 1));
+        TileKernel k = tile_kernel(cn, !p.gflow ? 0 : (p.dtaps ? 2 : 1), win);
         const int smem = cn * kTPlane * 4;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
