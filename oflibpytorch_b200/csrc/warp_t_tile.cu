@@ -1,4 +1,4 @@
-// W adjoint, tile-owned accumulation (the default for the plain warp).
+// W adjoint, tile-owned accumulation (the default, for the plain warp and for windowed frames).
 //
 // Adjoint of reference utils.py:541-555 (grid_sample bilinear / zeros / align_corners=True, i.e. ATen's
 // grid_sampler_2d_backward): gflow is a gather, gsrc the un-normalised splat of w * gout.
@@ -8,7 +8,7 @@
 // for 1.6 GB of gradient, l1tex__m_l1tex2xbar_req_cycles_active 70 %), and merging taps in registers reduces lanes, not
 // sectors.  Here a CTA owns a 32 x 32 tile of OUTPUT pixels and accumulates all its 4*C contributions per pixel into a
 // shared-memory window (64 x 52 per channel) that covers the tile's footprint in the source image, then flushes the
-// window ONCE with dense 16-byte REDs, skipping empty quads: about 20 sectors per 32 pixels instead of 93.
+// window ONCE with dense 16-byte REDs, skipping empty quads: 17 RED sectors per 32 pixels instead of 93 (ncu).
 //
 // Float atomics on shared memory are CAS loops on sm_100 (ATOMS.CAST.SPIN); 32-bit integer adds are native
 // (ATOMS.ADD, about 2 clk per warp-op, tools/microbench.cu).  The window therefore accumulates in FIXED POINT with a
