@@ -8,7 +8,7 @@
 //           taps all lie inside the image takes a path without tap predicates; bit-identical to the direct kernel.
 //   direct  (the general path: windows for padded / row-band warps, more than 4 channels, validity only): taps
 //           through the read-only path with explicit bounds predicates.
-//   staged  (opt-in, OFB_TMA=1): a CTA streams its tile's flow, reduces the bounding box of the sample positions and
+//   staged  (opt-in, OFB_TMA=1; OFB_TMA=2: persistent, double-buffered tile loop): a CTA streams its tile's flow, reduces the bounding box of the sample positions and
 //           has one thread issue TMA box copies (cp.async.bulk.tensor.3d) of that source region into shared memory,
 //           zero-filled outside the image by the TMA unit; taps are then LDS [reg + imm].  Parity-green but slower
 //           (0.52 of the HBM peak against 0.63 on the benchmark's flow field with 32 x 32 tiles and 64 x 48 boxes, 5 CTAs
@@ -616,6 +616,220 @@ __global__ void __launch_bounds__(256, OFB_ST_MINB) warp_t_fwd_staged_kernel(con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// staged forward, persistent and double-buffered (opt-in, OFB_TMA=2)
+// ------------------------------------------------------------------------------------------------
+// The same staging as above with the phases of consecutive tiles overlapped: a CTA walks tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...; while it evaluates tile k from stage k & 1, the TMA boxes of tile k + 1 are in flight into
+// the other stage and the flow of tile k + 2 is in flight into registers.  Needs 1..4 channels in one group.
+struct PipeCtl {
+    unsigned long long bar[2];      // one mbarrier per stage
+    int ox[2], oy[2], mode[2];      // per stage: box origin and 0 staged / 1 direct (footprint too large) / 2 nothing in bounds
+    int minx, maxx, miny, maxy;     // footprint reduction scratch
+};
+
+template <int CN, int VMODE>
+__global__ void __launch_bounds__(256, 2) warp_t_fwd_pipe_kernel(const WarpFwdParams p,
+                                                                 const __grid_constant__ CUtensorMap src_map,
+                                                                 const __grid_constant__ CUtensorMap mask_map,
+                                                                 const CoordCtx cc, const int tiles_x, const int tiles_y)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int kStage = kPlane * 4 * CN + (VMODE == 2 ? kMBoxW * kBoxH : 0);
+    constexpr int kStageAl = (kStage + 1023) & ~1023;
+    PipeCtl &ctl = *reinterpret_cast<PipeCtl *>(smem + 2 * kStageAl);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int HW = p.H * p.W;
+    const int ntiles = tiles_x * tiles_y * p.N;
+    const float wm1 = cc.dw.d, hm1 = cc.dh.d;
+
+    if (threadIdx.x == 0) {
+        mbar_init(reinterpret_cast<uint64_t *>(&ctl.bar[0]), 1);
+        mbar_init(reinterpret_cast<uint64_t *>(&ctl.bar[1]), 1);
+        ctl.minx = INT_MAX; ctl.miny = INT_MAX; ctl.maxx = INT_MIN; ctl.maxy = INT_MIN;
+    }
+    __syncthreads();
+
+    auto tile_xyn = [&](int t, int &x, int &y0, int &n) {
+        n = t / (tiles_x * tiles_y);
+        const int rem = t - n * (tiles_x * tiles_y);
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        x = tx * kTileW + (warp % kStWX) * 32 + lane;
+        y0 = ty * kTileH + (warp / kStWX) * kRows;
+    };
+    auto load_flow = [&](int t, float (&fx)[kRows], float (&fy)[kRows]) {
+        int x, y0, n;
+        tile_xyn(t, x, y0, n);
+        const float *fl = p.flow + (int64_t)n * p.flow_bs + min(x, p.W - 1);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const int yc = min(y0 + r, p.H - 1);
+            fx[r] = __ldg(fl + yc * p.W);
+            fy[r] = __ldg(fl + HW + yc * p.W);
+        }
+    };
+    // sample positions of tile t, footprint reduction, box copies into stage s (issued by thread 0)
+    auto stage_tile = [&](int t, int s, const float (&fx)[kRows], const float (&fy)[kRows], float (&ix)[kRows],
+                          float (&iy)[kRows]) {
+        int x, y0, n;
+        tile_xyn(t, x, y0, n);
+        const float xf = (float)x;
+        int minx = INT_MAX, maxx = INT_MIN, miny = INT_MAX, maxy = INT_MIN;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            sample_pos(cc, fx[r], fy[r], xf, (float)(y0 + r), ix[r], iy[r]);
+            const float fx0 = floorf(ix[r]), fy0 = floorf(iy[r]);
+            const bool any = (x < p.W) && (y0 + r < p.H) && fx0 >= -1.0f && fx0 <= wm1 && fy0 >= -1.0f && fy0 <= hm1;
+            if (any) {
+                const int xi = (int)fx0, yi = (int)fy0;
+                minx = min(minx, xi); maxx = max(maxx, xi); miny = min(miny, yi); maxy = max(maxy, yi);
+            }
+        }
+        minx = __reduce_min_sync(0xffffffffu, minx); maxx = __reduce_max_sync(0xffffffffu, maxx);
+        miny = __reduce_min_sync(0xffffffffu, miny); maxy = __reduce_max_sync(0xffffffffu, maxy);
+        if (lane == 0 && minx != INT_MAX) {
+            atomicMin(&ctl.minx, minx); atomicMax(&ctl.maxx, maxx);
+            atomicMin(&ctl.miny, miny); atomicMax(&ctl.maxy, maxy);
+        }
+        __syncthreads();                       // footprint complete; every thread is done with stage s (tile t - 2)
+        if (threadIdx.x == 0) {
+            int mode = 0;
+            if (ctl.minx == INT_MAX) mode = 2;
+            else if (ctl.maxx + 2 - (ctl.minx & ~3) > kBoxW || ctl.maxy - ctl.miny + 2 > kBoxH) mode = 1;
+            ctl.mode[s] = mode; ctl.ox[s] = ctl.minx & ~3; ctl.oy[s] = ctl.miny;
+            if (mode == 0) {
+                unsigned char *st = smem + s * kStageAl;
+                fence_proxy_async();           // the stage was last read through the generic proxy
+                mbar_expect_tx(reinterpret_cast<uint64_t *>(&ctl.bar[s]), (uint32_t)kStage);
+                tma_load_3d(st, &src_map, ctl.minx & ~3, ctl.miny, (p.src_bs == 0) ? 0 : n * p.C,
+                            reinterpret_cast<uint64_t *>(&ctl.bar[s]));
+                if (VMODE == 2)
+                    tma_load_3d(st + kPlane * 4 * CN, &mask_map, ctl.minx & ~15, ctl.miny, (p.src_mask_bs == 0) ? 0 : n,
+                                reinterpret_cast<uint64_t *>(&ctl.bar[s]));
+            }
+            ctl.minx = INT_MAX; ctl.miny = INT_MAX; ctl.maxx = INT_MIN; ctl.maxy = INT_MIN;
+        }
+        __syncthreads();                       // stage info published, scratch reset
+    };
+
+    const int t0 = blockIdx.x;
+    if (t0 >= ntiles) return;
+    float fxn[kRows], fyn[kRows], ix[kRows], iy[kRows], ixn[kRows], iyn[kRows];
+    load_flow(t0, fxn, fyn);
+    stage_tile(t0, 0, fxn, fyn, ix, iy);
+    if (t0 + (int)gridDim.x < ntiles) load_flow(t0 + gridDim.x, fxn, fyn);
+
+    unsigned phase = 0u;                        // bit s: parity of stage s's next barrier completion
+    for (int k = 0;; ++k) {
+        const int s = k & 1;
+        const int t = t0 + k * (int)gridDim.x, tn = t + (int)gridDim.x, tnn = tn + (int)gridDim.x;
+        if (tn < ntiles) stage_tile(tn, s ^ 1, fxn, fyn, ixn, iyn);
+        if (tnn < ntiles) load_flow(tnn, fxn, fyn);
+
+        // ---- evaluate tile t from stage s
+        int x, y0, n;
+        tile_xyn(t, x, y0, n);
+        const int mode = ctl.mode[s], ox = ctl.ox[s], oy = ctl.oy[s];
+        if (mode == 0) {                        // (CTA-uniform) the stage's barrier completes once per staged tile
+            mbar_wait(reinterpret_cast<uint64_t *>(&ctl.bar[s]), (phase >> s) & 1u);
+            phase ^= 1u << s;
+        }
+        if (mode == 1) {                        // footprint larger than the box: through global memory
+            if (x < p.W) {
+                const Window wn{0, 0, p.H, p.W, 0, 0, p.H, p.W};
+                ItemPtrs ip = item_ptrs(p, wn, n, 0);
+                if (VMODE != 2) ip.smask = nullptr;
+                const float *fl = p.flow + (int64_t)n * p.flow_bs + x;
+#pragma unroll 1
+                for (int r = 0; r < kRows; ++r) {
+                    const int y = y0 + r;
+                    if (y >= p.H) break;
+                    const PixGeom g = pix_geom<false>(ix[r], iy[r], wn);
+                    warp_pixel_direct<CN, VMODE != 0, false>(p, wn, ip, g, y * p.W + x, __ldg(fl + y * p.W),
+                                                            __ldg(fl + HW + y * p.W), 0, CN);
+                }
+            }
+        } else {
+            const float *tile = reinterpret_cast<const float *>(smem + s * kStageAl);
+            const uint8_t *mtile = smem + s * kStageAl + kPlane * 4 * CN;
+            const int mdx = ox - ((ox + 0) & ~15) ;          // payload-box column -> mask-box column (mask origin = minx & ~15)
+            float *out = p.out + (int64_t)n * p.C * HW + x;
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) {
+                const float fx0 = floorf(ix[r]), fy0 = floorf(iy[r]);
+                const bool any = mode == 0 && fx0 >= -1.0f && fx0 <= wm1 && fy0 >= -1.0f && fy0 <= hm1;
+                const bool st = (x < p.W) && (y0 + r < p.H);
+                const int xi = any ? (int)fx0 - ox : 0, yi = any ? (int)fy0 - oy : 0;
+                const int off = yi * kBoxW + xi;
+                const float ex = __fsub_rn(__fadd_rn(fx0, 1.0f), ix[r]), wx = __fsub_rn(ix[r], fx0);
+                const float sy = __fsub_rn(__fadd_rn(fy0, 1.0f), iy[r]), ny = __fsub_rn(iy[r], fy0);
+                const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
+                const int pix = (y0 + r) * p.W;
+                if (VMODE != 0) {
+                    float a, b, c, d;
+                    if (VMODE == 2) {
+                        const uint8_t *m = mtile + yi * kMBoxW + xi + mdx;
+                        a = m[0] ? 1.0f : 0.0f; b = m[1] ? 1.0f : 0.0f;
+                        c = m[kMBoxW] ? 1.0f : 0.0f; d = m[kMBoxW + 1] ? 1.0f : 0.0f;
+                    } else {
+                        const int gx = xi + ox, gy = yi + oy;
+                        const bool bx0 = gx >= 0, bx1 = gx + 1 <= p.W - 1, by0 = gy >= 0, by1 = gy + 1 <= p.H - 1;
+                        a = (bx0 && by0) ? 1.0f : 0.0f; b = (bx1 && by0) ? 1.0f : 0.0f;
+                        c = (bx0 && by1) ? 1.0f : 0.0f; d = (bx1 && by1) ? 1.0f : 0.0f;
+                    }
+                    float m = __fmul_rn(a, wnw);
+                    m = __fmaf_rn(b, wne, m);
+                    m = __fmaf_rn(c, wsw, m);
+                    m = __fmaf_rn(d, wse, m);
+                    bool ok = any && (m > p.thresh);
+                    if (st) {
+                        if (p.flow_mask) ok = ok && (__ldg(p.flow_mask + (int64_t)n * p.flow_mask_bs + pix + x) != 0);
+                        p.valid[(int64_t)n * HW + pix + x] = ok ? 1 : 0;
+                    }
+                }
+                const float *tp = tile + off;
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    float v = __fmul_rn(tp[c * kPlane], wnw);
+                    v = __fmaf_rn(tp[c * kPlane + 1], wne, v);
+                    v = __fmaf_rn(tp[c * kPlane + kBoxW], wsw, v);
+                    v = __fmaf_rn(tp[c * kPlane + kBoxW + 1], wse, v);
+                    v = any ? v : 0.0f;
+                    if (p.add_flow != 0.0f && c < 2 && st) {
+                        const float f = __ldg(p.flow + (int64_t)n * p.flow_bs + c * HW + pix + x);
+                        v = __fadd_rn(__fmul_rn(p.add_flow, f), v);
+                    }
+                    if (st) out[(int64_t)c * HW + pix] = v;
+                }
+            }
+        }
+        if (tn >= ntiles) break;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) { ix[r] = ixn[r]; iy[r] = iyn[r]; }
+    }
+}
+
+typedef void (*PipeKernel)(const WarpFwdParams, const CUtensorMap, const CUtensorMap, const CoordCtx, const int, const int);
+
+template <int CN>
+static PipeKernel pipe_kernel_for(int vmode)
+{
+    if (vmode == 0) return warp_t_fwd_pipe_kernel<CN, 0>;
+    if (vmode == 1) return warp_t_fwd_pipe_kernel<CN, 1>;
+    return warp_t_fwd_pipe_kernel<CN, 2>;
+}
+
+static PipeKernel pipe_kernel(int cn, int vmode)
+{
+    switch (cn) {
+        case 1: return pipe_kernel_for<1>(vmode);
+        case 2: return pipe_kernel_for<2>(vmode);
+        case 3: return pipe_kernel_for<3>(vmode);
+        default: return pipe_kernel_for<4>(vmode);
+    }
+}
+
 typedef void (*StagedKernel)(const WarpFwdParams, const CUtensorMap, const CUtensorMap, const int, const CoordCtx);
 
 template <int CN>
@@ -895,6 +1109,22 @@ static int warp_t_fwd_impl(const float *flow, int64_t flow_bs, float flow_sign,
                                  (uint64_t)((src_mask_bs == 0) ? 1 : N), kMBoxW, kBoxH, 1);
         else
             mask_map = src_maps[0];
+    }
+    static const bool use_pipe = getenv("OFB_TMA") != nullptr && atoi(getenv("OFB_TMA")) == 2;
+    if (staged && use_pipe && groups == 1) {
+        const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+        const int64_t ntiles = (int64_t)tiles_x * tiles_y * N;
+        if (ntiles <= 0x7fffffff) {
+            PipeKernel k = pipe_kernel(C, vmode);
+            const int stage = kPlane * 4 * C + (vmode == 2 ? kMBoxW * kBoxH : 0);
+            const int smem = 2 * ((stage + 1023) & ~1023) + (int)sizeof(PipeCtl) + 64;
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            const int ctas = (int)(ntiles < 148 * 2 ? ntiles : 148 * 2);
+            k<<<ctas, 256, smem, st>>>(p, src_maps[0], mask_map, cc, tiles_x, tiles_y);
+            OFB_CHECK_LAUNCH();
+            return 0;
+        }
     }
     if (staged) {
         const dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, N);

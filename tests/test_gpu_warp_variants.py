@@ -157,3 +157,19 @@ def test_broadcast_upstream_gradient_is_not_materialised():
     gf2, gs2 = ops()._warp_t_bwd(flow, 1.0, img, g1.contiguous(), 0.0, True, True)
     assert torch.equal(gf, gf2)
     assert_grad_close(gs, gs2, 'image gradient, broadcast vs dense gout')
+
+
+@pytest.mark.parametrize('mode', ['1', '2'])
+def test_tma_staged_forward_variants_keep_parity(mode):
+    """OFB_TMA=1 (TMA-staged tiles) and OFB_TMA=2 (persistent, double-buffered tile loop) are opt-in forward kernels
+    (slower than the default); the golden / oracle parity tests of the warp must pass with either.  The
+    switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OFB_TMA=mode)
+    out = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_parity.py'), '-q', '-x',
+                          '-k', 'warp_t or apply_flow or flow_apply_t or combine'],
+                         env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-500:]
