@@ -1,5 +1,5 @@
 """A/B of the W adjoint implementations on one box (tuning aid): register-merge (0), ring + RED flush (1),
-ring + TMA reduce flush (2), swept over the rows-per-task knob.  Prints ms per launch at the bench size and the
+ring + TMA reduce flush (2), tile-owned accumulation (7, the default), swept over the ring's rows-per-task knob.  Prints ms per launch at the bench size and the
 max deviation of gsrc / gflow from implementation 0.
 usage: python tools/ab_bwd.py [batch] [sigma]"""
 import sys
@@ -32,7 +32,7 @@ def run(impl, rows, steps=6):
 t0, gf0, gs0 = run(0, 24)
 print("impl 0 (register merge): %.3f ms" % t0, flush=True)
 scale = float(gs0.abs().max())
-for impl in (2, 3, 4, 5, 6):
+for impl in (1, 2, 7):
     for rows in (16, 24, 48):
         try:
             t, gf, gs = run(impl, rows)
