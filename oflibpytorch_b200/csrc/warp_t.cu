@@ -262,6 +262,34 @@ __global__ void __launch_bounds__(256) warp_fwd_early_kernel(const WarpFwdParams
     if (p.out_flags && last_n >= 0) publish_stats_lane(p.out_flags, last_n, p.N, all, masked);
 }
 
+#ifndef OFB_LEAN_PF
+#define OFB_LEAN_PF 128
+#endif
+// L2 prefetch of the lines the CTA launched `dist` slots later will stream (flow, payload rows, masks of its 64 x 16
+// pixel block): one 128-byte line per thread of a 256-thread CTA, fire-and-forget (no register lands, no scoreboard).
+// Used by the lean forward only: the same prologue made the direct kernel with result flags (combine_flows) 4 % slower
+// and left the tile adjoint unchanged (both measured at distance 16..256).
+template <int CN>
+__device__ __forceinline__ void prefetch_ahead(const WarpFwdParams &p, const int dist, const int cta_rows)
+{
+    const int W = p.W, HW = p.H * p.W;
+    const long long lin = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + dist;
+    const long long total = (long long)gridDim.x * gridDim.y * gridDim.z;
+    if (lin >= total) return;
+    const int pz = (int)(lin / ((long long)gridDim.x * gridDim.y));
+    const int rem = (int)(lin - (long long)pz * gridDim.x * gridDim.y);
+    const int py = rem / (int)gridDim.x, px = rem - py * (int)gridDim.x;
+    const int t = threadIdx.x;
+    const int row = min(py * cta_rows + (t & 15), p.H - 1), half = (t >> 4) & 1, what = t >> 5;   // 8 groups of 32
+    const int col = min(px * 64 + half * 32, W - 1);
+    const void *a = nullptr;
+    if (what < 2) a = p.flow + (int64_t)pz * p.flow_bs + (int64_t)what * HW + row * W + col;
+    else if (what < 2 + CN) a = p.src + (int64_t)pz * p.src_bs + (int64_t)(what - 2) * HW + row * W + col;
+    else if (what == 2 + CN && p.src_mask && half == 0) a = p.src_mask + (int64_t)pz * p.src_mask_bs + row * W + col;
+    else if (what == 3 + CN && p.flow_mask && half == 0) a = p.flow_mask + (int64_t)pz * p.flow_mask_bs + row * W + col;
+    if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+}
+
 template <int CN, bool WANT_VALID, bool WIN, bool STATS = false>
 __global__ void __launch_bounds__(256, OFB_FWD_MINB) warp_t_fwd_direct_kernel(const WarpFwdParams p, const CoordCtx cc)
 {
@@ -314,9 +342,6 @@ __global__ void __launch_bounds__(256, OFB_FWD_MINB) warp_t_fwd_direct_kernel(co
 #ifndef OFB_LEAN_MINB
 #define OFB_LEAN_MINB 8
 #endif
-#ifndef OFB_LEAN_PF
-#define OFB_LEAN_PF 128
-#endif
 constexpr int kLeanRows = OFB_LEAN_ROWS;
 
 //   * WANT_D: the kernel also writes d out[c] / d ix and d out[c] / d iy (2C planes).  The adjoint's flow gradient is
@@ -352,24 +377,7 @@ __global__ void __launch_bounds__(256, OFB_LEAN_MINB) warp_t_fwd_lean_kernel(con
     // register file full of loads in flight (DESIGN 3 "What bounds W"); turning that CTA's first-touch misses into L2
     // hits shortens every wait: -11 % at C = 3, -7 % at C = 2, -13 % at C = 4 (batch 32 x 1080p; distances 16..450 within
     // 1 %, 900: -6 %, 2400: +28 %), +12 % at C = 1, which is therefore left out.
-    if (OFB_LEAN_PF > 0 && !WIN && CN >= 2) {
-        const long long lin = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + OFB_LEAN_PF;
-        const long long total = (long long)gridDim.x * gridDim.y * gridDim.z;
-        if (lin < total) {
-            const int pz = (int)(lin / ((long long)gridDim.x * gridDim.y));
-            const int rem = (int)(lin - (long long)pz * gridDim.x * gridDim.y);
-            const int py = rem / (int)gridDim.x, px = rem - py * (int)gridDim.x;
-            const int t = threadIdx.x;
-            const int row = min(py * (4 * kLeanRows) + (t & 15), p.H - 1), half = (t >> 4) & 1, what = t >> 5;   // 8 groups of 32
-            const int col = min(px * 64 + half * 32, W - 1);
-            const void *a = nullptr;
-            if (what < 2) a = p.flow + (int64_t)pz * p.flow_bs + (int64_t)what * HW + row * W + col;
-            else if (what < 2 + CN) a = p.src + (int64_t)pz * p.src_bs + (int64_t)(what - 2) * HW + row * W + col;
-            else if (what == 2 + CN && p.src_mask && half == 0) a = p.src_mask + (int64_t)pz * p.src_mask_bs + row * W + col;
-            else if (what == 3 + CN && p.flow_mask && half == 0) a = p.flow_mask + (int64_t)pz * p.flow_mask_bs + row * W + col;
-            if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-        }
-    }
+    if (OFB_LEAN_PF > 0 && !WIN && CN >= 2) prefetch_ahead<CN>(p, OFB_LEAN_PF, 4 * kLeanRows);
     float fx[kLeanRows], fy[kLeanRows];
     {
         const int q0 = y0 * W + min(x, W - 1);
