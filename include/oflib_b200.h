@@ -60,6 +60,9 @@ void ofb_launch_count_reset(void);
  *   key 4  S forward: 1 = deterministic merge (64-bit fixed-point accumulation: float outputs bit-identical from run
  *          to run, about 3x slower), 0 = float atomics (default).  ofb_splat_s_workspace follows the mode.
  *   key 5  W forward: 0 = lean kernel (default), 1 = direct kernel (the general path: windows, > 4 channels)
+ *   key 6  W adjoint (tile kernel): 1 = the kernel zero-fills the payload gradient itself, tile rows ahead of its
+ *          REDs, instead of a memset pass (less DRAM traffic, measured slower; uses one workspace per device, so calls
+ *          must not overlap on two streams of one device), 0 = memset (default)
  * Returns 0, or OFB_EINVAL for an unknown key.  Process-wide, not thread-safe. */
 int ofb_set_option(int key, int value);
 

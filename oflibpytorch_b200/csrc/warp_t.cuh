@@ -101,6 +101,7 @@ struct WarpBwdParams {
     const int32_t *sel;   // device-side early-out decision (ofb_early_decide), or nullptr
     const float *dtaps;   // (N, 2C, H, W) d out[c] / d(ix, iy) saved by the forward (ofb_warp_t_fwd_d), or nullptr
     int gout_bcast;       // 1: gout is ONE value broadcast over (N, C, H, W) -- the gradient of out.sum(), never materialised
+    int32_t *za;          // zero-ahead workspace of the tile adjoint (warp_t_tile.cu), or nullptr
 };
 
 // Predicated fire-and-forget reduction: `@p red.global.add.f32 [a + imm], v` -- no branch, no return value.

@@ -27,6 +27,7 @@
 
 namespace ofb {
 
+int g_bwd_za = 0;            // tile adjoint zero-fills the payload gradient itself (warp_t_tile.cu), key 6
 int g_bwd_impl = -1;        // tuning knob (ofb_set_option): -1 auto (= 7), 0 register-merge kernel, 1 ring + RED flush, 2 ring + TMA,
                             // 7 tile-owned fixed-point accumulation (warp_t_tile.cu)
 int g_bwd_band_rows = 24;   // output rows per warp task
@@ -362,12 +363,14 @@ int warp_t_bwd_ring_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStrea
 
 // Tuning knobs (profiling sweeps; the defaults are the measured best).  key 1: W adjoint implementation
 // (-1 auto, 0 register-merge, 1 ring + RED flush, 2 ring + TMA reduce flush); key 2: output rows per warp task;
-// key 4: deterministic splat merge (64-bit fixed point) on/off; key 5: W forward (0 lean kernel, 1 direct kernel).
+// key 4: deterministic splat merge (64-bit fixed point) on/off; key 5: W forward (0 lean kernel, 1 direct kernel);
+// key 6: zero-ahead mode of the tile adjoint on/off.
 extern "C" int ofb_set_option(int key, int value)
 {
     if (key == 1) { ofb::g_bwd_impl = value; return 0; }
     if (key == 2) { ofb::g_bwd_band_rows = value; return 0; }
     if (key == 4) { ofb::g_splat_det = value ? 1 : 0; return 0; }
     if (key == 5) { ofb::g_fwd_impl = value; return 0; }
+    if (key == 6) { ofb::g_bwd_za = value ? 1 : 0; return 0; }
     return OFB_EINVAL;
 }

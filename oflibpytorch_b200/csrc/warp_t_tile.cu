@@ -26,6 +26,7 @@
 namespace ofb {
 
 extern int g_bwd_impl;
+extern int g_bwd_za;
 
 constexpr int kTT = 32;                    // tile edge (output pixels): 8 warps x 4 rows, lane = column
 constexpr int kTRows = 4;                  // rows per thread
@@ -68,7 +69,31 @@ __device__ __forceinline__ void red_add_v4(float *a, float x, float y, float z, 
 // GFLOW: 0 no flow gradient, 1 from the payload taps (global gathers), 2 from the derivative planes the forward saved
 // WIN:   the flow / gout / gflow tensors are a window of a larger frame and src / gsrc a stored region of it (struct Window,
 //        warp_t.cuh: padded apply with cut, row bands); everything about the taps then lives in stored-region coordinates
-template <int CN, int GFLOW, bool WIN>
+#ifndef OFB_TILE_ZROWS
+#define OFB_TILE_ZROWS 4
+#endif
+constexpr int kZRows = OFB_TILE_ZROWS;     // zero-ahead distance in tile rows
+
+__device__ __forceinline__ int ld_acquire(const int *a)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+    return v;
+}
+
+// ZA ("zero ahead", opt-in: ofb_set_option(6, 1)): the kernel zero-fills the payload gradient itself.  Tile rows are
+// numbered through the batch (R = n * tiles_y + ty); the CTA of tile (R, tx) first stores zeros over the region of tile
+// (R + kZRows, tx) and, behind its first barrier, one thread fences and bumps za[R + kZRows]; before a CTA issues REDs it
+// waits until every tile row its footprint touches is complete (za[R'] == tiles_x).  CTAs are dispatched in launch
+// order, so the rows waited for belong to CTAs that are already running and whose zero-fill does not wait for anything
+// (the forward-progress argument of a decoupled look-back scan).  The host zero-fills the first kZRows tile rows; a tile
+// whose footprint reaches kZRows or more tile rows DOWN cannot wait (those rows belong to later CTAs): it leaves its
+// payload-gradient part to warp_t_bwd_tile_deferred_kernel.
+// Measured (ncu, 32 x 3 x 1080p): it does what it was built for -- the zeros are still in L2 when the REDs arrive, DRAM
+// reads 2.91 -> 2.13 GB (no read for the read-modify-write), writes unchanged, no 0.8 GB memset -- and it is SLOWER:
+// 1.08 ms against 0.93 + 0.108 (memset) = 1.03 ms; without the waits (wrong results) 1.03 ms.  The kernel is not bound by
+// DRAM bytes, and the zero stores cost inside it what they cost the memset.  Hence opt-in, not the default.
+template <int CN, int GFLOW, bool WIN, bool ZA = false>
 __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(const WarpBwdParams p, const CoordCtx cc, const int c_off,
                                                                  const int accumulate_gflow, const int vec_ok)
 {
@@ -102,6 +127,28 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
         for (int i = threadIdx.x; i < CN * kTPlane / 4; i += 256) w4[i] = make_int4(0, 0, 0, 0);
         if (threadIdx.x == 0) {
             ctl.minx = INT_MAX; ctl.miny = INT_MAX; ctl.maxx = INT_MIN; ctl.maxy = INT_MIN; ctl.amax = 0u;
+        }
+    }
+    const int Rg = ZA ? n * (int)gridDim.y + (int)blockIdx.y : 0;              // this tile's row, counted through the batch
+    bool za_signal = false;
+    if (ZA) {
+        const int Rt = Rg + kZRows;
+        if (Rt < (int)(gridDim.y * gridDim.z)) {
+            const int nz = Rt / (int)gridDim.y, tyz = Rt - nz * (int)gridDim.y;
+            const int zy = tyz * kTT + (threadIdx.x >> 3), zx = blockIdx.x * kTT + (threadIdx.x & 7) * 4;
+            if (zy < H && zx < W) {
+                float *z = p.gsrc + (int64_t)nz * p.gsrc_bs + (zy * W + zx);
+#pragma unroll
+                for (int c = 0; c < CN; ++c) {
+                    if (vec_ok) {
+                        *reinterpret_cast<float4 *>(z + c * HW) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    } else {
+                        for (int k = 0; k < 4; ++k)
+                            if (zx + k < W) z[c * HW + k] = 0.0f;
+                    }
+                }
+            }
+            za_signal = true;
         }
     }
 
@@ -144,6 +191,9 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
         miny = __reduce_min_sync(0xffffffffu, miny); maxy = __reduce_max_sync(0xffffffffu, maxy);
         amax = __reduce_max_sync(0xffffffffu, amax);
         __syncthreads();                                   // the control block is initialised
+        // release by ONE thread behind the barrier (the pattern of a cooperative-groups grid sync: the fence is cumulative
+        // over what the barrier ordered before it); a fence in every thread showed up as 7 % membar stalls
+        if (ZA && za_signal && threadIdx.x == 0) { __threadfence(); atomicAdd(p.za + (Rg + kZRows), 1); }
         if (lane == 0) {
             if (minx != INT_MAX) {
                 atomicMin(&ctl.minx, minx); atomicMax(&ctl.maxx, maxx);
@@ -158,7 +208,24 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
     const unsigned amax = ctl.amax;
     const bool nothing = ctl.minx == INT_MAX || amax == 0u;                 // no tap in the image, or a zero gradient
     // fixed point needs the footprint inside the window and a finite gradient; otherwise float REDs per tap
-    const bool tiled = !nothing && ex_w <= kTWin && ex_h <= kTWinH && amax < 0x7f800000u;
+    bool tiled = !nothing && ex_w <= kTWin && ex_h <= kTWinH && amax < 0x7f800000u;
+    bool za_defer = false;
+    if (ZA && !nothing) {
+        const int r0 = n * (int)gridDim.y + (ctl.miny >> 5), r1 = n * (int)gridDim.y + (ctl.maxy >> 5);
+        za_defer = r1 >= Rg + kZRows;                       // CTA-uniform
+        if (za_defer) {
+            if (threadIdx.x == 0) {
+                const int slot = atomicAdd(p.za + (gridDim.y * gridDim.z), 1);
+                p.za[gridDim.y * gridDim.z + 1 + slot] = (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+            }
+        } else {
+            for (int R = max(r0, kZRows) + (int)threadIdx.x; R <= r1; R += 256)
+                while (ld_acquire(p.za + R) < (int)gridDim.x) {}
+            if (!tiled) __syncthreads();                    // the float REDs of phase 2 come before the next barrier
+        }
+    }
+    if (za_defer) tiled = false;
+    const bool skip_red = nothing || za_defer;              // no contribution to the payload gradient from this CTA
     // amax in [2^E, 2^(E+1)), E = e - 127 clamped to >= -100: scale 2^(19-E), inverse 2^(E-19)
     const int e = max((int)(amax >> 23), 27);
     const float scale = __uint_as_float((unsigned)(127 + 19 + 127 - e) << 23);
@@ -221,7 +288,7 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
                     atomicAdd(wp + c * kTPlane + kTWin, __float2int_rn(wsw * gs));
                     atomicAdd(wp + c * kTPlane + kTWin + 1, __float2int_rn(wse * gs));
                 }
-            } else if (!nothing) {
+            } else if (!skip_red) {
                 const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
 #pragma unroll
                 for (int c = 0; c < CN; ++c) {
@@ -270,7 +337,7 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
                     __stcg(gf + (HW + pix), ry);
                 }
             }
-            if (!nothing) {
+            if (!skip_red) {
                 const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
                 int *wp = win + ((yi - oy) * kTWin + (xi - ox));       // only dereferenced for in-image taps
 #pragma unroll
@@ -327,6 +394,56 @@ __global__ void __launch_bounds__(256, OFB_TILE_MINB) warp_t_bwd_tile_kernel(con
 
 typedef void (*TileKernel)(const WarpBwdParams, const CoordCtx, const int, const int, const int);
 
+// Deferred pass of the zero-ahead mode: the payload-gradient part of the tiles listed in za[ntr + 1 ...] (footprints that
+// reach kZRows or more tile rows down), as plain float REDs per tap.  Launched behind the tile kernel, when everything is
+// zero-filled; the list is almost always empty.
+__global__ void __launch_bounds__(256) warp_t_bwd_tile_deferred_kernel(const WarpBwdParams p, const CoordCtx cc, const int tiles_x,
+                                                                       const int tiles_y)
+{
+    const int ntr = tiles_y * p.N;
+    const int count = p.za[ntr];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = p.W, H = p.H, HW = H * W;
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+        const int tile = p.za[ntr + 1 + e];
+        const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+        const int x = tx * kTT + lane;
+        if (x >= W) continue;
+        const float *fl = p.flow + (int64_t)n * p.flow_bs;
+        const float *go = p.gout_bcast ? p.gout : p.gout + (int64_t)n * p.C * HW;
+        float *gsrc = p.gsrc + (int64_t)n * p.gsrc_bs;
+        for (int r = 0; r < kTRows; ++r) {
+            const int y = ty * kTT + warp * kTRows + r;
+            if (y >= H) break;
+            const int q = y * W + x;
+            const float ix = round_trip_unchecked(__fmaf_rn(-cc.sign, __ldg(fl + q), (float)x), cc.dw);
+            const float iy = round_trip_unchecked(__fmaf_rn(-cc.sign, __ldg(fl + (HW + q)), (float)y), cc.dh);
+            const int xi = __float2int_rd(ix), yi = __float2int_rd(iy);
+            const float x0 = floorf(ix), y0f = floorf(iy);
+            const float ex = __fsub_rn(__fadd_rn(x0, 1.0f), ix), wx = __fsub_rn(ix, x0);
+            const float sy = __fsub_rn(__fadd_rn(y0f, 1.0f), iy), ny = __fsub_rn(iy, y0f);
+            const float wnw = __fmul_rn(ex, sy), wne = __fmul_rn(wx, sy), wsw = __fmul_rn(ex, ny), wse = __fmul_rn(wx, ny);
+            const bool bx0 = (unsigned)xi < (unsigned)W, bx1 = (unsigned)(xi + 1) < (unsigned)W;
+            const bool by0 = (unsigned)yi < (unsigned)H, by1 = (unsigned)(yi + 1) < (unsigned)H;
+            const int o = yi * W + xi;
+            for (int c = 0; c < p.C; ++c) {
+                const float g = p.gout_bcast ? go[0] : __ldg(go + ((int64_t)c * HW + q));
+                float *t = gsrc + ((int64_t)c * HW + o);
+                if (bx0 && by0) red_add_f32(t, wnw * g);
+                if (bx1 && by0) red_add_f32(t + 1, wne * g);
+                if (bx0 && by1) red_add_f32(t + W, wsw * g);
+                if (bx1 && by1) red_add_f32(t + W + 1, wse * g);
+            }
+        }
+    }
+}
+
+template <int CN>
+static TileKernel tile_kernel_za(int gflow)
+{
+    return gflow ? warp_t_bwd_tile_kernel<CN, 1, false, true> : warp_t_bwd_tile_kernel<CN, 0, false, true>;
+}
+
 template <int CN>
 static TileKernel tile_kernel_for(int gflow, bool win)
 {
@@ -345,6 +462,29 @@ static TileKernel tile_kernel(int cn, int gflow, bool win)
     }
 }
 
+// Workspace of the zero-ahead mode: one buffer per device, grown on demand, never freed.  Calls on different streams of
+// one device would share it, which is why the mode is opt-in and documented as single-stream.
+static cudaError_t za_workspace(size_t bytes, int32_t **out)
+{
+    static int32_t *buf[64] = {nullptr};
+    static size_t cap[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (cap[dev] < bytes) {
+        cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;      // an allocation is legal inside a relaxed capture
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        if (buf[dev]) cudaFree(buf[dev]);
+        e = cudaMalloc(reinterpret_cast<void **>(&buf[dev]), bytes);
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        if (e != cudaSuccess) { buf[dev] = nullptr; cap[dev] = 0; return e; }
+        cap[dev] = bytes;
+    }
+    *out = buf[dev];
+    return cudaSuccess;
+}
+
 // Returns 0 when it handled the call, 1 when the caller must use the register-merge kernel, or a CUDA error.
 int warp_t_bwd_tile_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStream_t st)
 {
@@ -356,6 +496,44 @@ int warp_t_bwd_tile_launch(const WarpBwdParams &p, const CoordCtx &cc, cudaStrea
     if (win && (p.dtaps || p.gout_bcast)) return 1;
     const int64_t HWs = (int64_t)wn.sh * wn.sw;
     const int64_t item_bytes = (int64_t)p.C * HWs * 4;
+    // zero-ahead mode (see the kernel): plain frame, one channel group, a payload gradient per item, payload taps
+    const int tiles_x = (p.W + kTT - 1) / kTT, tiles_y = (p.H + kTT - 1) / kTT;
+    if (g_bwd_za && !win && p.C <= 4 && p.gsrc_bs != 0 && !p.dtaps && tiles_y >= kZRows &&
+        (int64_t)tiles_x * tiles_y * p.N < (1 << 30)) {
+        const int ntr = tiles_y * p.N;
+        const size_t ws_bytes = sizeof(int32_t) * ((size_t)ntr + 1 + (size_t)tiles_x * tiles_y * p.N);
+        int32_t *ws = nullptr;
+        cudaError_t e = za_workspace(ws_bytes, &ws);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemsetAsync(ws, 0, sizeof(int32_t) * ((size_t)ntr + 1), st);
+        // the first kZRows tile rows (all in item 0) have no CTA ahead of them: rows [0, 32 kZRows) of every plane
+        if (e == cudaSuccess)
+            e = cudaMemset2DAsync(p.gsrc, (size_t)HWs * 4, 0, (size_t)min(kZRows * kTT, p.H) * p.W * 4, (size_t)p.C, st);
+        if (e != cudaSuccess) return (int)e;
+        WarpBwdParams q = p;
+        q.za = ws;
+        const int vec_ok = (p.W % 4 == 0) && aligned16(p.gsrc) && (p.gsrc_bs % 4 == 0);
+        TileKernel k;
+        switch (p.C) {
+            case 1: k = tile_kernel_za<1>(p.gflow != nullptr); break;
+            case 2: k = tile_kernel_za<2>(p.gflow != nullptr); break;
+            case 3: k = tile_kernel_za<3>(p.gflow != nullptr); break;
+            default: k = tile_kernel_za<4>(p.gflow != nullptr); break;
+        }
+        const int smem = p.C * kTPlane * 4;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) {
+            k<<<dim3(tiles_x, tiles_y, p.N), 256, smem, st>>>(q, cc, 0, 0, vec_ok);
+            ++g_launches;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) {
+            warp_t_bwd_tile_deferred_kernel<<<148 * 4, 256, 0, st>>>(q, cc, tiles_x, tiles_y);
+            ++g_launches;
+            e = cudaGetLastError();
+        }
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     {
         cudaError_t e = cudaMemsetAsync(p.gsrc, 0, (size_t)(p.gsrc_bs == 0 ? item_bytes : item_bytes * p.N), st);
         if (e != cudaSuccess) return (int)e;

@@ -27,6 +27,7 @@ def _reset_knobs():
     yield
     lib().ofb_set_option(1, -1)
     lib().ofb_set_option(5, 0)
+    lib().ofb_set_option(6, 0)
     ops().set_save_derivatives(False)
 
 
@@ -173,3 +174,27 @@ def test_tma_staged_forward_variants_keep_parity(mode):
                           '-k', 'warp_t or apply_flow or flow_apply_t or combine'],
                          env=env, capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-500:]
+
+
+@pytest.mark.parametrize('c,gflow', [(3, True), (1, True), (4, False), (2, True)])
+def test_tile_adjoint_zero_ahead_mode_matches_the_memset_path(c, gflow):
+    """ofb_set_option(6, 1): the tile adjoint zero-fills the payload gradient itself, tile rows ahead of the REDs
+    (warp_t_tile.cu).  Same results as the default path and the oracle, including tiles whose footprint lies far below
+    them (deferred pass), far above, outside the field, and a field whose last tile row is partial."""
+    from oracle import oracle as orc
+    n, h, w = 3, 300, 200                              # 10 tile rows (the last one partial), 7 tile columns
+    flow, img, gout = case(n, c, h, w, 41)
+    flow[0, 1, 20:50, 30:150] = -220.0                 # samples 220 rows further down: deferred tiles
+    flow[1, 1, 250:290, 10:100] = 240.0                # far above
+    flow[2, 0, 100:120, :] = 900.0                     # outside
+    res = []
+    for za in (0, 1, 1):                               # twice: the counters are re-initialised per call
+        lib().ofb_set_option(6, za)
+        res.append(ops()._warp_t_bwd(flow, 1.0, img, gout, 0.0, gflow, True))
+    gf_o, gs_o = orc.raw_warp_t_bwd(flow.cpu(), img.cpu(), gout.cpu())
+    for gf, gs in res[1:]:
+        assert_grad_close(gs, gs_o, 'gsrc (zero-ahead) vs oracle')
+        assert_grad_close(gs, res[0][1], 'gsrc (zero-ahead) vs memset path')
+        if gflow:
+            assert torch.equal(gf, res[0][0])
+            assert_grad_close(gf, gf_o, 'gflow')
