@@ -323,6 +323,9 @@ __device__ __forceinline__ void red_vec(float *acc, int q, const AccVec<KP> &a, 
     }
 }
 
+#ifndef OFB_SPLAT_PF
+#define OFB_SPLAT_PF 128
+#endif
 #ifndef OFB_SPLAT_MINB
 #define OFB_SPLAT_MINB 3
 #endif
@@ -349,6 +352,36 @@ __global__ void __launch_bounds__(256, OFB_SPLAT_MINB) splat_accumulate_v1_kerne
     float *accb = SPLIT ? p.acc_bad + (int64_t)blockIdx.z * p.acc_h * p.W : nullptr;
     asm volatile("" : "+l"(cx), "+l"(cy), "+l"(data), "+l"(dmask), "+l"(fmask), "+l"(acc), "+l"(accb));
 
+    // L2 prefetch of the source rows the CTA launched OFB_SPLAT_PF slots later will stream (coordinates, payload planes,
+    // masks), fire-and-forget -- the kernel is bound by memory latency at 3 CTAs per SM (see warp_t_fwd_lean_kernel)
+    if (OFB_SPLAT_PF > 0) {
+        const long long lin = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + OFB_SPLAT_PF;
+        const long long total = (long long)gridDim.x * gridDim.y * gridDim.z;
+        if (lin < total) {
+            const int pz = (int)(lin / ((long long)gridDim.x * gridDim.y));
+            const int rem = (int)(lin - (long long)pz * gridDim.x * gridDim.y);
+            const int py = rem / (int)gridDim.x, px = rem - py * (int)gridDim.x;
+            const int nn = n0 + pz;
+            constexpr int kRows = 4 * kSplatRows, kPlane = 2 * kRows;        // two 128-byte lines per row and plane
+            constexpr int kLines = (2 + C) * kPlane;
+            for (int idx = threadIdx.x; idx < kLines + 2 * kRows; idx += 256) {
+                const void *a = nullptr;
+                if (idx < kLines) {
+                    const int pl = idx / kPlane, j = idx - pl * kPlane;
+                    const int o = min(py * kRows + (j >> 1), p.H - 1) * p.W + min(px * 64 + (j & 1) * 32, p.W - 1);
+                    if (pl == 0) a = p.cx + (int64_t)nn * p.coord_bs + o;
+                    else if (pl == 1) a = p.cy + (int64_t)nn * p.coord_bs + o;
+                    else a = p.data + (int64_t)nn * p.data_bs + ((int64_t)(pl - 2) * HW + o);
+                } else {
+                    const int j = idx - kLines, which = j / kRows;
+                    const int o = min(py * kRows + (j - which * kRows), p.H - 1) * p.W + min(px * 64, p.W - 1);
+                    if (which == 0 && HAS_BAD) a = p.data_mask + (int64_t)nn * p.data_mask_bs + o;
+                    if (which == 1 && p.flow_mask) a = p.flow_mask + (int64_t)nn * p.flow_mask_bs + o;
+                }
+                if (a) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+        }
+    }
     AccVec<KP> carry;                                    // south-tap sums waiting for the next source row
 #pragma unroll
     for (int j = 0; j < KP; ++j) carry.v[j] = 0.0f;
